@@ -1,0 +1,647 @@
+// faa_cabi.cu - host side of the C ABI declared in include/faa_b200.h:
+// policy compilation (level -> magnitude -> Pillow fixed-point / LUT / blend parameters),
+// the MT19937 parity sampler, normalisation tables, device-table management and launches.
+// There is NO CPU implementation of the pixel path in this library: every compute entry
+// point fails with FAA_ERR_NO_DEVICE when no CUDA device is usable.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/faa_b200.h"
+#include "faa_kernels.cuh"
+
+using namespace faa;
+
+static_assert(sizeof(faa_sample_t) == 16 && sizeof(Sample) == 16, "sample record is 16 bytes");
+static_assert(sizeof(faa_box_t) == 8 && sizeof(Box) == 8, "box record is 8 bytes");
+static_assert(sizeof(OpRec) == 32, "op record is 32 bytes");
+static_assert(sizeof(faa_rng_t) == sizeof(RngCfg), "rng config layout");
+
+// ------------------------------------------------------------------ errors --
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(FAA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+// --------------------------------------------------------------- op table --
+struct OpInfo { const char* name; double low, high; int draw; };
+// augment_list(for_autoaug=True): augmentations.py:156-182
+static const OpInfo kOps[FAA_NUM_OPS] = {
+    {"ShearX", -0.3, 0.3, FAA_DRAW_MIRROR},      {"ShearY", -0.3, 0.3, FAA_DRAW_MIRROR},
+    {"TranslateX", -0.45, 0.45, FAA_DRAW_MIRROR}, {"TranslateY", -0.45, 0.45, FAA_DRAW_MIRROR},
+    {"Rotate", -30, 30, FAA_DRAW_MIRROR},        {"AutoContrast", 0, 1, FAA_DRAW_NONE},
+    {"Invert", 0, 1, FAA_DRAW_NONE},             {"Equalize", 0, 1, FAA_DRAW_NONE},
+    {"Solarize", 0, 256, FAA_DRAW_NONE},         {"Posterize", 4, 8, FAA_DRAW_NONE},
+    {"Contrast", 0.1, 1.9, FAA_DRAW_NONE},       {"Color", 0.1, 1.9, FAA_DRAW_NONE},
+    {"Brightness", 0.1, 1.9, FAA_DRAW_NONE},     {"Sharpness", 0.1, 1.9, FAA_DRAW_NONE},
+    {"Cutout", 0, 0.2, FAA_DRAW_BOX},            {"CutoutAbs", 0, 20, FAA_DRAW_BOX},
+    {"Posterize2", 0, 4, FAA_DRAW_NONE},         {"TranslateXAbs", 0, 10, FAA_DRAW_MIRROR},
+    {"TranslateYAbs", 0, 10, FAA_DRAW_MIRROR},
+};
+
+// ---------------------------------------------------------- compile helpers --
+static inline int32_t fix16(double z) { return (int32_t)std::floor(z * 65536.0 + 0.5); }   // Pillow FIX()
+
+// Python's round(x, 15): correctly rounded decimal round trip
+static double py_round15(double x) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.15f", x);
+    return strtod(buf, nullptr);
+}
+// Python float %: result takes the sign of the divisor
+static double py_fmod(double a, double b) {
+    double r = std::fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+// ImagingScaleAffine axis table with accumulation (Geometry.c); returns the integer shift
+// or INT32_MIN when the mapping is not a pure shift
+static int32_t unit_scale_shift(int n, double scale, double offset) {
+    double o = offset + scale * 0.5;
+    bool have = false; int32_t shift = 0;
+    for (int i = 0; i < n; ++i) {
+        int c = (o < 0.0) ? -1 : (int)o;
+        if (c >= 0 && c < n) {
+            if (!have) { shift = c - i; have = true; }
+            else if (c - i != shift) return INT32_MIN;
+        }
+        o += scale;
+    }
+    return have ? shift : (int32_t)FAA_MAX_DIM * 2;     // nothing maps inside: everything is fill
+}
+
+struct Compiled { OpRec rec; int err; };   // err: 0 ok, FAA_ERR_UNKNOWN_OP, FAA_ERR_MAGNITUDE, FAA_ERR_UNSUPPORTED
+
+static void set_affine(OpRec& r, const double m[6], int H, int W, int& err) {
+    if (m[1] == 0.0 && m[3] == 0.0) {                     // Pillow: pure scale -> ImagingScaleAffine
+        if (m[0] != 1.0 || m[4] != 1.0) { err = FAA_ERR_UNSUPPORTED; return; }
+        int32_t dx = unit_scale_shift(W, 1.0, m[2]), dy = unit_scale_shift(H, 1.0, m[5]);
+        if (dx == INT32_MIN || dy == INT32_MIN) { err = FAA_ERR_UNSUPPORTED; return; }
+        if (dx == 0 && dy == 0) { r.kind = K_NONE; return; }
+        r.kind = K_SHIFT; r.a[0] = dx; r.a[1] = dy;
+        return;
+    }
+    r.kind = K_AFFINE;                                    // Pillow affine_fixed
+    r.a[0] = fix16(m[0]); r.a[1] = fix16(m[1]); r.a[2] = fix16(m[2] + m[0] * 0.5 + m[1] * 0.5);
+    r.a[3] = fix16(m[3]); r.a[4] = fix16(m[4]); r.a[5] = fix16(m[5] + m[3] * 0.5 + m[4] * 0.5);
+}
+
+static void set_blend(OpRec& r, int kind, double v) {
+    float a = (float)v;                                   // _blend passes a C float to ImagingBlend
+    r.kind = kind;
+    memcpy(&r.a[0], &a, 4);
+    r.a[1] = !(a >= 0.0f && a <= 1.0f);
+}
+
+// apply_augment (augmentations.py:192-194) + the op's own parameter handling, at compile time
+static Compiled compile_op(int op_id, double level, int sign, int H, int W) {
+    Compiled c; memset(&c, 0, sizeof c);
+    OpRec& r = c.rec; r.kind = K_NONE;
+    if (op_id < 0 || op_id >= FAA_NUM_OPS) { c.err = FAA_ERR_UNKNOWN_OP; return c; }
+    const OpInfo& info = kOps[op_id];
+    r.draw = info.draw;
+    double v = level * (info.high - info.low) + info.low;
+    // the reference's per-op asserts (CutoutAbs' is commented out, augmentations.py:127)
+    bool has_assert = !(op_id == FAA_AUTOCONTRAST || op_id == FAA_INVERT || op_id == FAA_EQUALIZE || op_id == FAA_CUTOUT_ABS);
+    if (has_assert && !(info.low <= v && v <= info.high)) { c.err = FAA_ERR_MAGNITUDE; return c; }
+    if (info.draw == FAA_DRAW_MIRROR && sign) v = -v;
+    double m[6] = {1, 0, 0, 0, 1, 0};
+    switch (op_id) {
+    case FAA_SHEAR_X: m[1] = v; set_affine(r, m, H, W, c.err); break;                        // :17
+    case FAA_SHEAR_Y: m[3] = v; set_affine(r, m, H, W, c.err); break;                        // :24
+    case FAA_TRANSLATE_X: m[2] = v * (double)W; set_affine(r, m, H, W, c.err); break;        // :31-32
+    case FAA_TRANSLATE_Y: m[5] = v * (double)H; set_affine(r, m, H, W, c.err); break;        // :39-40
+    case FAA_TRANSLATE_X_ABS: m[2] = v; set_affine(r, m, H, W, c.err); break;                // :47
+    case FAA_TRANSLATE_Y_ABS: m[5] = v; set_affine(r, m, H, W, c.err); break;                // :54
+    case FAA_ROTATE: {                                                                        // :61 + PIL Image.rotate
+        double angle = py_fmod(v, 360.0);
+        if (angle == 0.0) break;                                                              // copy fast path
+        if (angle == 180.0 || ((angle == 90.0 || angle == 270.0) && W == H)) { c.err = FAA_ERR_UNSUPPORTED; break; }
+        double cx = W / 2.0, cy = H / 2.0;
+        double t = -(angle * (M_PI / 180.0));                                                 // -math.radians(angle)
+        m[0] = py_round15(std::cos(t)); m[1] = py_round15(std::sin(t)); m[2] = 0.0;
+        m[3] = py_round15(-std::sin(t)); m[4] = py_round15(std::cos(t)); m[5] = 0.0;
+        double t2 = m[0] * (-cx) + m[1] * (-cy) + m[2];
+        double t5 = m[3] * (-cx) + m[4] * (-cy) + m[5];
+        m[2] = t2 + cx; m[5] = t5 + cy;
+        set_affine(r, m, H, W, c.err);
+        break;
+    }
+    case FAA_AUTOCONTRAST: r.kind = K_AUTOCONTRAST; break;                                    // :65
+    case FAA_EQUALIZE: r.kind = K_EQUALIZE; break;                                            // :73
+    case FAA_INVERT: r.kind = K_LUT; r.a[0] = 0; r.a[1] = 0xFF; break;                        // :69
+    case FAA_SOLARIZE: {                                                                      // :82  (i < v with float v)
+        double th = std::ceil(v);
+        r.kind = K_LUT; r.a[0] = (int32_t)(th < 0 ? 0 : th > 256 ? 256 : th); r.a[1] = 0xFF;
+        break;
+    }
+    case FAA_POSTERIZE: case FAA_POSTERIZE2: {                                                // :87-88, :93-94
+        int bits = (int)v;
+        int mask = ~((1 << (8 - bits)) - 1) & 0xFF;
+        r.kind = K_LUT; r.a[0] = 256; r.a[1] = mask;
+        break;
+    }
+    case FAA_CONTRAST: set_blend(r, K_CONTRAST, v); break;                                    // :99
+    case FAA_COLOR: set_blend(r, K_COLOR, v); break;                                          // :104
+    case FAA_BRIGHTNESS: set_blend(r, K_BRIGHTNESS, v); break;                                // :109
+    case FAA_SHARPNESS: set_blend(r, K_SHARPNESS, v); break;                                  // :114
+    case FAA_CUTOUT: {                                                                        // :117-123
+        if (v <= 0.0) { r.draw = FAA_DRAW_NONE; break; }                                      // returns before any draw
+        double px = v * (double)W;
+        r.kind = K_CUTOUT; memcpy(&r.a[0], &px, 8);
+        break;
+    }
+    case FAA_CUTOUT_ABS: {                                                                    // :126-144
+        if (v < 0.0) { r.draw = FAA_DRAW_NONE; break; }
+        r.kind = K_CUTOUT; memcpy(&r.a[0], &v, 8);
+        break;
+    }
+    }
+    if (c.err) r.kind = K_NONE;
+    return c;
+}
+
+// ------------------------------------------------------------------ policy --
+struct DeviceTable { OpRec* d_ops = nullptr; };
+
+struct faa_policy {
+    int n_sub = 0, n_op = 0;
+    std::vector<int32_t> op_ids;
+    std::vector<double> probs, levels;
+    std::mutex mu;
+    std::map<std::pair<int, int>, std::vector<Compiled>> host_tables;   // (H,W) -> [n_sub][n_op][2]
+    std::map<std::pair<int, int>, DeviceTable> dev_tables;
+    double* d_probs = nullptr;
+    float* d_norm = nullptr;            // [3][256]
+    float norm_mean[3] = {-1e30f, 0, 0}, norm_std[3] = {0, 0, 0};
+    float norm_host[768];
+    // scratch of faa_augment_host
+    void* d_in = nullptr; size_t d_in_bytes = 0;
+    void* d_out = nullptr; size_t d_out_bytes = 0;
+    void* h_in_stage = nullptr; size_t h_in_bytes = 0;
+    void* h_out_stage = nullptr; size_t h_out_bytes = 0;
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+};
+
+static const std::vector<Compiled>& host_table(faa_policy* p, int H, int W) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto key = std::make_pair(H, W);
+    auto it = p->host_tables.find(key);
+    if (it != p->host_tables.end()) return it->second;
+    std::vector<Compiled> t((size_t)p->n_sub * p->n_op * 2);
+    for (int s = 0; s < p->n_sub; ++s)
+        for (int j = 0; j < p->n_op; ++j)
+            for (int sg = 0; sg < 2; ++sg) {
+                size_t k = (size_t)s * p->n_op + j;
+                t[k * 2 + sg] = compile_op(p->op_ids[k], p->levels[k], sg, H, W);
+            }
+    return p->host_tables.emplace(key, std::move(t)).first->second;
+}
+
+static int first_table_error(const std::vector<Compiled>& t, std::string& what) {
+    for (size_t i = 0; i < t.size(); ++i)
+        if (t[i].err) {
+            what = "sub-policy " + std::to_string(i / 2) + " (flattened op index)";
+            return t[i].err;
+        }
+    return 0;
+}
+
+extern "C" {
+
+int faa_abi_version(void) { return FAA_ABI_VERSION; }
+const char* faa_last_error(void) { return g_err.c_str(); }
+uint64_t faa_launch_count(void) { return g_launches.load(); }
+
+int faa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int faa_op_id_from_name(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < FAA_NUM_OPS; ++i) if (strcmp(name, kOps[i].name) == 0) return i;
+    return -1;
+}
+const char* faa_op_name(int op_id) { return (op_id >= 0 && op_id < FAA_NUM_OPS) ? kOps[op_id].name : nullptr; }
+int faa_op_range(int op_id, double* low, double* high) {
+    if (op_id < 0 || op_id >= FAA_NUM_OPS) return fail(FAA_ERR_UNKNOWN_OP, "unknown op id");
+    if (low) *low = kOps[op_id].low;
+    if (high) *high = kOps[op_id].high;
+    return FAA_OK;
+}
+
+int faa_policy_create(const int32_t* op_ids, const double* probs, const double* levels, int n_sub, int n_op,
+                      faa_policy_t** out) {
+    if (!op_ids || !probs || !levels || !out) return fail(FAA_ERR_VALUE, "null argument");
+    if (n_sub <= 0 || n_sub > 65535) return fail(FAA_ERR_VALUE, "n_sub must be in [1, 65535]");
+    if (n_op <= 0 || n_op > FAA_MAX_POLICY_OPS) return fail(FAA_ERR_VALUE, "n_op must be in [1, 8]");
+    faa_policy* p = new faa_policy();
+    p->n_sub = n_sub; p->n_op = n_op;
+    size_t n = (size_t)n_sub * n_op;
+    p->op_ids.assign(op_ids, op_ids + n);
+    p->probs.assign(probs, probs + n);
+    p->levels.assign(levels, levels + n);
+    *out = p;
+    return FAA_OK;
+}
+
+int faa_policy_destroy(faa_policy_t* p) {
+    if (!p) return FAA_OK;
+    for (auto& kv : p->dev_tables) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
+    if (p->d_probs) cudaFree(p->d_probs);
+    if (p->d_norm) cudaFree(p->d_norm);
+    if (p->d_in) cudaFree(p->d_in);
+    if (p->d_out) cudaFree(p->d_out);
+    if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
+    if (p->h_out_stage) cudaFreeHost(p->h_out_stage);
+    for (int i = 0; i < 2; ++i) {
+        if (p->side[i]) cudaStreamDestroy(p->side[i]);
+        if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+    }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    delete p;
+    return FAA_OK;
+}
+
+int faa_policy_dims(const faa_policy_t* p, int* n_sub, int* n_op) {
+    if (!p) return fail(FAA_ERR_VALUE, "null policy");
+    if (n_sub) *n_sub = p->n_sub;
+    if (n_op) *n_op = p->n_op;
+    return FAA_OK;
+}
+
+static int check_shape(int h, int w) {
+    if (h <= 0 || w <= 0 || h > FAA_MAX_DIM || w > FAA_MAX_DIM) return fail(FAA_ERR_VALUE, "image size out of range");
+    return FAA_OK;
+}
+
+int faa_policy_compiled_op(faa_policy_t* p, int h, int w, int sub, int op, int sign, int32_t out8[8]) {
+    if (!p || !out8) return fail(FAA_ERR_VALUE, "null argument");
+    if (int e = check_shape(h, w)) return e;
+    if (sub < 0 || sub >= p->n_sub || op < 0 || op >= p->n_op) return fail(FAA_ERR_VALUE, "index out of range");
+    const Compiled& c = host_table(p, h, w)[((size_t)sub * p->n_op + op) * 2 + (sign ? 1 : 0)];
+    memcpy(out8, &c.rec, 32);
+    if (c.err) return fail(c.err, "op cannot be compiled (unknown op / magnitude out of range)");
+    return FAA_OK;
+}
+
+int faa_policy_draw_kind(const faa_policy_t* p, int sub, int op) {
+    if (!p || sub < 0 || sub >= p->n_sub || op < 0 || op >= p->n_op) return -1;
+    int id = p->op_ids[(size_t)sub * p->n_op + op];
+    if (id < 0 || id >= FAA_NUM_OPS) return -1;
+    if (id == FAA_CUTOUT) {
+        double v = p->levels[(size_t)sub * p->n_op + op] * (kOps[id].high - kOps[id].low) + kOps[id].low;
+        if (v <= 0.0) return FAA_DRAW_NONE;
+    }
+    return kOps[id].draw;
+}
+
+int faa_cutout_box(const faa_policy_t* pc, int h, int w, int sub, int op, double ux, double uy, faa_box_t* out) {
+    faa_policy* p = const_cast<faa_policy*>(pc);
+    if (!p || !out) return fail(FAA_ERR_VALUE, "null argument");
+    if (int e = check_shape(h, w)) return e;
+    if (sub < 0 || sub >= p->n_sub || op < 0 || op >= p->n_op) return fail(FAA_ERR_VALUE, "index out of range");
+    const Compiled& c = host_table(p, h, w)[((size_t)sub * p->n_op + op) * 2];
+    if (c.err) return fail(c.err, "op cannot be compiled");
+    if (c.rec.kind != K_CUTOUT) return fail(FAA_ERR_VALUE, "op draws no box");
+    double v; memcpy(&v, &c.rec.a[0], 8);
+    Box b = cutout_box(w, h, v, ux, uy);
+    memcpy(out, &b, 8);
+    return FAA_OK;
+}
+
+// ------------------------------------------------------------ MT19937 replay --
+struct MT {
+    uint32_t* s; uint32_t* pos;
+    explicit MT(uint32_t st[625]) : s(st), pos(st + 624) {}
+    void refill() {
+        const uint32_t N = 624, M = 397, UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
+        uint32_t y; uint32_t kk;
+        for (kk = 0; kk < N - M; ++kk) { y = (s[kk] & UP) | (s[kk + 1] & LO); s[kk] = s[kk + M] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+        for (; kk < N - 1; ++kk) { y = (s[kk] & UP) | (s[kk + 1] & LO); s[kk] = s[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+        y = (s[N - 1] & UP) | (s[0] & LO); s[N - 1] = s[M - 1] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        *pos = 0;
+    }
+    uint32_t u32() {
+        if (*pos >= 624) refill();
+        uint32_t y = s[(*pos)++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    double real53() {   // CPython random.random() and numpy legacy random_sample(): same formula
+        uint32_t a = u32() >> 5, b = u32() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    uint32_t below(uint32_t n) {   // CPython _randbelow_with_getrandbits
+        int k = 32 - __builtin_clz(n);
+        uint32_t r;
+        do { r = u32() >> (32 - k); } while (r >= n);
+        return r;
+    }
+};
+
+int faa_sample_policy_mt(const faa_policy_t* pc, int batch, int h, int w, uint32_t py_state[625],
+                         uint32_t np_state[625], faa_sample_t* out_samples, faa_box_t* out_boxes) {
+    faa_policy* p = const_cast<faa_policy*>(pc);
+    if (!p || !py_state || !np_state || !out_samples || !out_boxes) return fail(FAA_ERR_VALUE, "null argument");
+    if (batch < 0) return fail(FAA_ERR_VALUE, "negative batch");
+    if (int e = check_shape(h, w)) return e;
+    if (py_state[624] > 624 || np_state[624] > 624) return fail(FAA_ERR_VALUE, "bad MT19937 position");
+    const std::vector<Compiled>& tab = host_table(p, h, w);
+    MT py(py_state), np(np_state);
+    for (int i = 0; i < batch; ++i) {
+        faa_sample_t s; memset(&s, 0, sizeof s);
+        uint32_t sub = py.below((uint32_t)p->n_sub);                          // random.choice, data.py:259
+        s.sub = (uint16_t)sub;
+        for (int j = 0; j < p->n_op; ++j) {
+            faa_box_t& bx = out_boxes[(size_t)i * p->n_op + j];
+            bx.x0 = bx.y0 = 0; bx.x1 = bx.y1 = -1;
+            size_t k = (size_t)sub * p->n_op + j;
+            if (py.real53() > p->probs[k]) continue;                           // data.py:261
+            const Compiled& c0 = tab[k * 2];
+            if (c0.err) return fail(c0.err, std::string("applied op is invalid: ") +
+                                    (c0.err == FAA_ERR_UNKNOWN_OP ? "unknown op" : "magnitude out of range / unsupported"));
+            s.gate |= (uint8_t)(1u << j);
+            if (c0.rec.draw == FAA_DRAW_MIRROR) {
+                if (py.real53() > 0.5) s.sign |= (uint8_t)(1u << j);           // augmentations.py:15 ...
+            } else if (c0.rec.draw == FAA_DRAW_BOX) {
+                double ux = np.real53(), uy = np.real53();                     // augmentations.py:131-132
+                double v; memcpy(&v, &c0.rec.a[0], 8);
+                Box b = cutout_box(w, h, v, ux, uy);
+                memcpy(&bx, &b, 8);
+            }
+        }
+        out_samples[i] = s;
+    }
+    return FAA_OK;
+}
+
+// ------------------------------------------------------------ device tables --
+static int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(FAA_ERR_NO_DEVICE, "no CUDA device available: fast_autoaugment_b200 has no CPU fallback");
+    }
+    return FAA_OK;
+}
+
+static int device_table(faa_policy* p, int H, int W, bool need_valid, const OpRec** d_ops) {
+    const std::vector<Compiled>& t = host_table(p, H, W);
+    if (need_valid) {
+        std::string what;
+        if (int e = first_table_error(t, what))
+            return fail(e, "policy contains an op that cannot run (" + what + "): unknown op or magnitude out of range");
+    }
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto key = std::make_pair(H, W);
+    auto it = p->dev_tables.find(key);
+    if (it == p->dev_tables.end()) {
+        std::vector<OpRec> flat(t.size());
+        for (size_t i = 0; i < t.size(); ++i) flat[i] = t[i].rec;
+        DeviceTable d;
+        CK(cudaMalloc(&d.d_ops, flat.size() * sizeof(OpRec)));
+        CK(cudaMemcpy(d.d_ops, flat.data(), flat.size() * sizeof(OpRec), cudaMemcpyHostToDevice));
+        it = p->dev_tables.emplace(key, d).first;
+    }
+    if (!p->d_probs) {
+        CK(cudaMalloc(&p->d_probs, p->probs.size() * sizeof(double)));
+        CK(cudaMemcpy(p->d_probs, p->probs.data(), p->probs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    *d_ops = it->second.d_ops;
+    return FAA_OK;
+}
+
+// ToTensor + Normalize exactly as torch computes them in fp32 (data.py:42-43):
+// x = u8 / 255 ; (x - mean) / std.  Also decides whether one fused multiply-add reproduces
+// the rounded result for every byte value in the requested output dtype.
+static uint16_t bits16(int dtype, float v) {
+    if (dtype == FAA_F16) { __half h = __float2half_rn(v); return __half_as_ushort(h); }
+    __nv_bfloat16 b = __float2bfloat16_rn(v); return __bfloat16_as_ushort(b);
+}
+
+static int normalisation(faa_policy* p, const faa_tail_t* tail, AugParams& P, cudaStream_t stream) {
+    bool same = true;
+    for (int c = 0; c < 3; ++c) same = same && p->norm_mean[c] == tail->mean[c] && p->norm_std[c] == tail->std[c];
+    if (!p->d_norm) { CK(cudaMalloc(&p->d_norm, 768 * sizeof(float))); same = false; }
+    if (!same) {
+        for (int c = 0; c < 3; ++c) {
+            if (!(tail->std[c] != 0.0f)) return fail(FAA_ERR_VALUE, "std must be non-zero");
+            for (int u = 0; u < 256; ++u) {
+                volatile float x = (float)u / 255.0f;
+                volatile float y = x - tail->mean[c];
+                volatile float z = y / tail->std[c];
+                p->norm_host[c * 256 + u] = z;
+            }
+            p->norm_mean[c] = tail->mean[c]; p->norm_std[c] = tail->std[c];
+        }
+        CK(cudaMemcpyAsync(p->d_norm, p->norm_host, 768 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    P.norm_tab = p->d_norm;
+    bool fma_ok = tail->out_dtype == FAA_F16 || tail->out_dtype == FAA_BF16;
+    for (int c = 0; c < 3; ++c) {
+        double sc = 1.0 / (255.0 * (double)tail->std[c]);
+        double bi = -(double)tail->mean[c] / (double)tail->std[c];
+        P.scale[c] = (float)sc; P.bias[c] = (float)bi;
+        if (fma_ok)
+            for (int u = 0; u < 256 && fma_ok; ++u) {
+                float f = fmaf((float)u, P.scale[c], P.bias[c]);
+                if (bits16(tail->out_dtype, f) != bits16(tail->out_dtype, p->norm_host[c * 256 + u])) fma_ok = false;
+            }
+    }
+    P.use_tab = fma_ok ? 0 : 1;
+    return FAA_OK;
+}
+
+static int out_elem_size(int dtype) { return dtype == FAA_F32 ? 4 : dtype == FAA_U8_HWC ? 1 : 2; }
+
+static int check_tail(const faa_tail_t* tail) {
+    if (!tail) return fail(FAA_ERR_VALUE, "null tail");
+    if (tail->out_h <= 0 || tail->out_w <= 0 || tail->out_h > FAA_MAX_DIM || tail->out_w > FAA_MAX_DIM)
+        return fail(FAA_ERR_VALUE, "output size out of range");
+    if (tail->out_dtype < 0 || tail->out_dtype > FAA_U8_HWC) return fail(FAA_ERR_VALUE, "bad out_dtype");
+    return FAA_OK;
+}
+
+int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t* tail, const faa_rng_t* rng,
+                      faa_sample_t* d_samples, faa_box_t* d_boxes, void* stream) {
+    if (!p || !rng || !d_samples || !d_boxes) return fail(FAA_ERR_VALUE, "null argument");
+    if (int e = check_shape(h, w)) return e;
+    if (int e = check_tail(tail)) return e;
+    if (int e = ensure_device()) return e;
+    const OpRec* d_ops = nullptr;
+    if (int e = device_table(p, h, w, true, &d_ops)) return e;
+    PhiloxParams P;
+    P.ops = d_ops; P.probs = p->d_probs; memcpy(&P.rng, rng, sizeof(RngCfg));
+    P.samples = reinterpret_cast<Sample*>(d_samples); P.boxes = reinterpret_cast<Box*>(d_boxes);
+    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.n_sub = p->n_sub; P.n_op = p->n_op;
+    CK(launch_philox(P, (cudaStream_t)stream));
+    if (batch > 0) g_launches++;
+    return FAA_OK;
+}
+
+static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch,
+                          int h, int w, const faa_tail_t* tail, const faa_sample_t* d_samples,
+                          const faa_box_t* d_boxes, const faa_rng_t* rng, int op_base, const int32_t* d_partner,
+                          float lam, float oml, int apply_tail, void* stream) {
+    if (!p || (!d_in_all && batch > 0) || (!d_out && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
+    if (batch < 0 || first < 0 || first + batch > n_all) return fail(FAA_ERR_VALUE, "bad batch range");
+    if (int e = check_shape(h, w)) return e;
+    if (int e = check_tail(tail)) return e;
+    if (!d_samples && !rng) return fail(FAA_ERR_VALUE, "need either resolved samples or an rng config");
+    if (op_base < 0 || op_base >= p->n_op) return fail(FAA_ERR_VALUE, "op_base out of range");
+    if (tail->out_dtype == FAA_U8_HWC && d_partner) return fail(FAA_ERR_UNSUPPORTED, "mixup needs a float output");
+    if (int e = ensure_device()) return e;
+    const OpRec* d_ops = nullptr;
+    // resolved samples can only reference ops the host sampler validated; Philox can pick anything
+    if (int e = device_table(p, h, w, d_samples == nullptr, &d_ops)) return e;
+    AugParams P; memset(&P, 0, sizeof P);
+    P.in = d_in_all; P.out = d_out; P.ops = d_ops; P.probs = p->d_probs;
+    P.samples = reinterpret_cast<const Sample*>(d_samples); P.boxes = reinterpret_cast<const Box*>(d_boxes);
+    P.partner = d_partner;
+    if (rng) memcpy(&P.rng, rng, sizeof(RngCfg));
+    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w;
+    P.n_sub = p->n_sub; P.n_op = p->n_op; P.op_base = op_base; P.first = first;
+    P.apply_tail = apply_tail; P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
+    P.lam = lam; P.one_minus_lam = oml;
+    if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, (cudaStream_t)stream)) return e; }
+    P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
+    CK(launch_augment(P, tail->out_dtype, (cudaStream_t)stream));
+    if (batch > 0) g_launches++;
+    return FAA_OK;
+}
+
+int faa_augment(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, int h, int w, const faa_tail_t* tail,
+                const faa_sample_t* d_samples, const faa_box_t* d_boxes, const faa_rng_t* rng, int op_base,
+                void* stream) {
+    if (!p) return fail(FAA_ERR_VALUE, "null policy");
+    // intermediate launch of a chained policy = not the last 2-op window
+    int apply_tail = (op_base + FAA_MAX_FUSED_OPS >= p->n_op) ? 1 : 0;
+    if (!apply_tail && tail && (tail->out_dtype != FAA_U8_HWC || tail->out_h != h || tail->out_w != w))
+        return fail(FAA_ERR_VALUE, "intermediate launches of a chained policy must write uint8 HWC at the input size");
+    return augment_common(p, d_in, batch, 0, d_out, batch, h, w, tail, d_samples, d_boxes, rng, op_base, nullptr,
+                          1.0f, 0.0f, apply_tail, stream);
+}
+
+int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch, int h,
+                      int w, const faa_tail_t* tail, const faa_sample_t* d_samples_all, const faa_box_t* d_boxes_all,
+                      const faa_rng_t* rng, const int32_t* d_partner, float lam, float one_minus_lam, void* stream) {
+    if (!p) return fail(FAA_ERR_VALUE, "null policy");
+    if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "fused mixup supports policies of at most 2 ops");
+    if (!(lam >= 0.0f && lam <= 1.0f)) return fail(FAA_ERR_MAGNITUDE, "lam must be in [0, 1]");   // aug_mixup.py:20
+    return augment_common(p, d_in_all, n_all, first, d_out, batch, h, w, tail, d_samples_all, d_boxes_all, rng, 0,
+                          d_partner, lam, one_minus_lam, 1, stream);
+}
+
+int faa_mixup(const void* d_data, void* d_out, const int64_t* d_perm, int batch, int64_t n_per_sample, int dtype,
+              float lam, float one_minus_lam, void* stream) {
+    if ((!d_data || !d_out || !d_perm) && batch > 0) return fail(FAA_ERR_VALUE, "null argument");
+    if (batch < 0 || n_per_sample < 0) return fail(FAA_ERR_VALUE, "negative size");
+    if (dtype < 0 || dtype > FAA_F32) return fail(FAA_ERR_VALUE, "bad dtype");
+    if (int e = ensure_device()) return e;
+    CK(launch_mixup(d_data, d_out, d_perm, batch, n_per_sample, dtype, lam, one_minus_lam, (cudaStream_t)stream));
+    if (batch > 0 && n_per_sample > 0) g_launches++;
+    return FAA_OK;
+}
+
+// ------------------------------------------------------------- host buffers --
+static int grow_dev(void** ptr, size_t* have, size_t need) {
+    if (*have >= need) return FAA_OK;
+    if (*ptr) { CK(cudaFree(*ptr)); *ptr = nullptr; *have = 0; }
+    CK(cudaMalloc(ptr, need));
+    *have = need;
+    return FAA_OK;
+}
+static int grow_pinned(void** ptr, size_t* have, size_t need) {
+    if (*have >= need) return FAA_OK;
+    if (*ptr) { CK(cudaFreeHost(*ptr)); *ptr = nullptr; *have = 0; }
+    CK(cudaMallocHost(ptr, need));
+    *have = need;
+    return FAA_OK;
+}
+static bool is_pinned(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_out_keep, int batch, int h, int w,
+                     const faa_tail_t* tail, const faa_rng_t* rng, void* stream_v) {
+    if (!p || !h_in || !rng) return fail(FAA_ERR_VALUE, "null argument");
+    if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "host-buffer entry supports policies of at most 2 ops");
+    if (int e = check_shape(h, w)) return e;
+    if (int e = check_tail(tail)) return e;
+    if (int e = ensure_device()) return e;
+    if (batch <= 0) return FAA_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const size_t in_img = (size_t)h * w * 3;
+    const size_t out_img = (size_t)tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
+    if (int e = grow_dev(&p->d_in, &p->d_in_bytes, in_img * batch)) return e;
+    void* d_out = d_out_keep;
+    if (!d_out) { if (int e = grow_dev(&p->d_out, &p->d_out_bytes, out_img * batch)) return e; d_out = p->d_out; }
+    for (int i = 0; i < 2; ++i) {
+        if (!p->side[i]) CK(cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking));
+        if (!p->ev_join[i]) CK(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    if (!p->ev_fork) CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+
+    // pageable buffers are staged through pinned memory (synchronous host copies)
+    const bool in_pinned = is_pinned(h_in);
+    const bool out_pinned = !h_out || is_pinned(h_out);
+    const uint8_t* src = h_in;
+    if (!in_pinned) {
+        if (int e = grow_pinned(&p->h_in_stage, &p->h_in_bytes, in_img * batch)) return e;
+        memcpy(p->h_in_stage, h_in, in_img * batch);
+        src = (const uint8_t*)p->h_in_stage;
+    }
+    void* dst = h_out;
+    if (h_out && !out_pinned) {
+        if (int e = grow_pinned(&p->h_out_stage, &p->h_out_bytes, out_img * batch)) return e;
+        dst = p->h_out_stage;
+    }
+
+    // chunked pipeline on two side streams: H2D(c+1) overlaps kernel(c) and D2H(c)
+    int chunks = batch >= 64 ? 8 : (batch >= 8 ? 2 : 1);
+    CK(cudaEventRecord(p->ev_fork, stream));
+    CK(cudaStreamWaitEvent(p->side[0], p->ev_fork, 0));
+    CK(cudaStreamWaitEvent(p->side[1], p->ev_fork, 0));
+    for (int c = 0; c < chunks; ++c) {
+        int b0 = (int)((long long)batch * c / chunks), b1 = (int)((long long)batch * (c + 1) / chunks);
+        if (b1 <= b0) continue;
+        cudaStream_t s = p->side[c & 1];
+        CK(cudaMemcpyAsync((uint8_t*)p->d_in + in_img * b0, src + in_img * b0, in_img * (b1 - b0), cudaMemcpyHostToDevice, s));
+        if (int e = augment_common(p, (const uint8_t*)p->d_in, batch, b0, (uint8_t*)d_out + out_img * b0, b1 - b0, h, w,
+                                   tail, nullptr, nullptr, rng, 0, nullptr, 1.0f, 0.0f, 1, s)) return e;
+        if (dst) CK(cudaMemcpyAsync((uint8_t*)dst + out_img * b0, (uint8_t*)d_out + out_img * b0, out_img * (b1 - b0), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventRecord(p->ev_join[i], p->side[i]));
+        CK(cudaStreamWaitEvent(stream, p->ev_join[i], 0));
+    }
+    if (h_out && !out_pinned) {
+        CK(cudaStreamSynchronize(stream));
+        memcpy(h_out, p->h_out_stage, out_img * batch);
+    }
+    return FAA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+// faa_core.cuh - per-pixel arithmetic of the augmentation hot path, shared by the
+// sm_100a kernels (faa_kernels.cu) and by the host-side emulation used in the CPU
+// tests (tests/emu).  Every function states the reference call it reproduces
+// (file:line relative to kakaobrain/fast-autoaugment @ 2424224) and the Pillow /
+// torchvision arithmetic behind that call.
+//
+// Design: the raw uint8 HWC image is READ-ONLY.  A sub-policy is evaluated lazily
+// from the output pixel back to the raw image:
+//     value<2>(x,y) = op2( value<1>(.) ),  value<1>(x,y) = op1( value<0>(.) ),  value<0> = raw
+// Geometric ops remap the coordinate, per-channel ops go through a 3x256 byte LUT built
+// once per image (static LUTs, AutoContrast/Equalize from the histogram, Brightness /
+// Contrast blends), Color and Cutout are evaluated in registers, Sharpness evaluates its
+// 3x3 neighbourhood one level down.  No intermediate image is ever materialised, so the
+// whole chain needs no second image buffer and no barrier between ops; only the ops that
+// need whole-image statistics (AutoContrast, Equalize, Contrast) cost one extra pass.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FAA_HD __host__ __device__ __forceinline__
+#else
+#define FAA_HD inline
+#endif
+
+namespace faa {
+
+// ------------------------------------------------------------------ records --
+enum Kind : int32_t {
+    K_NONE = 0,          // identity (gate not passed, Rotate by 0, Cutout with v<=0 ...)
+    K_AFFINE = 1,        // a[0..5]: Pillow affine_fixed 16.16 coefficients
+    K_SHIFT = 2,         // a[0]=dx, a[1]=dy : out[y][x] = in[y+dy][x+dx]
+    K_LUT = 3,           // a[0]=solarize threshold (0..256), a[1]=AND mask : static per-channel LUT
+    K_AUTOCONTRAST = 4,  // histogram -> fp64 LUT
+    K_EQUALIZE = 5,      // histogram -> integer prefix LUT
+    K_BRIGHTNESS = 6,    // a[0]=fp32 bits of alpha, a[1]=clip flag ; blend with 0
+    K_COLOR = 7,         //   "   blend with luma
+    K_CONTRAST = 8,      //   "   blend with int(mean luma + .5) of the whole image
+    K_SHARPNESS = 9,     //   "   blend with 3x3 SMOOTH
+    K_CUTOUT = 10        // a[0..1]=fp64 bits of the side length in pixels; box comes per sample
+};
+
+struct OpRec {           // 32 bytes, one per (sub-policy, op slot, sign variant)
+    int32_t kind;
+    int32_t a[6];
+    int32_t draw;        // enum faa_draw of the *named* op (kept even when kind==K_NONE)
+};
+
+struct Box { int16_t x0, y0, x1, y1; };       // inclusive, unclipped (== faa_box_t)
+
+struct Sample {                               // == faa_sample_t
+    uint16_t sub; uint8_t gate; uint8_t sign;
+    int8_t crop_dy; int8_t crop_dx; uint8_t flip; uint8_t reserved;
+    int16_t zero_box[4];
+};
+
+constexpr uint32_t kCutoutRGB = 125u | (123u << 8) | (114u << 16);   // augmentations.py:140
+
+// kind classes
+FAA_HD bool kind_uses_lut(int k)   { return k == K_LUT || k == K_AUTOCONTRAST || k == K_EQUALIZE ||
+                                            k == K_BRIGHTNESS || k == K_CONTRAST; }
+FAA_HD bool kind_needs_hist(int k) { return k == K_AUTOCONTRAST || k == K_EQUALIZE; }
+FAA_HD bool kind_needs_mean(int k) { return k == K_CONTRAST; }
+FAA_HD bool kind_is_pointwise(int k) { return k == K_NONE || kind_uses_lut(k) || k == K_COLOR || k == K_CUTOUT; }
+
+// ------------------------------------------------------------ float helpers --
+// Non-contracted fp32 / fp64 steps (Pillow is compiled for x86-64 SSE2: no FMA).
+FAA_HD float f_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+FAA_HD float f_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+FAA_HD double d_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+FAA_HD double d_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+FAA_HD float bits_to_float(int32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(b);
+#else
+    union { int32_t i; float f; } u; u.i = b; return u.f;
+#endif
+}
+FAA_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// Pillow Image.blend (Blend.c), one byte: fp32, truncation; clip only when alpha is
+// outside [0,1].  Serves ImageEnhance.*.enhance -> augmentations.py:99,104,109,114.
+FAA_HD uint32_t blend_u8(uint32_t deg, uint32_t px, float alpha, bool clip) {
+    float d = (float)(int)deg;
+    float t = f_add(d, f_mul(alpha, (float)((int)px - (int)deg)));
+    if (clip) {
+        if (t <= 0.0f) return 0u;
+        if (t >= 255.0f) return 255u;
+    }
+    return (uint32_t)(int)t;
+}
+
+// Pillow RGB->L (Convert.c rgb2l): ImageEnhance.Color / Contrast degenerate images.
+FAA_HD uint32_t luma_of(uint32_t p) {
+    return (19595u * (p & 255u) + 38470u * ((p >> 8) & 255u) + 7471u * ((p >> 16) & 255u) + 0x8000u) >> 16;
+}
+
+FAA_HD uint32_t apply_lut(const uint8_t* lut, uint32_t p) {
+    return (uint32_t)lut[p & 255u] | ((uint32_t)lut[256 + ((p >> 8) & 255u)] << 8) |
+           ((uint32_t)lut[512 + ((p >> 16) & 255u)] << 16);
+}
+
+FAA_HD uint32_t color_px(uint32_t p, float alpha, bool clip) {      // augmentations.py:102-104
+    uint32_t l = luma_of(p);
+    return blend_u8(l, p & 255u, alpha, clip) | (blend_u8(l, (p >> 8) & 255u, alpha, clip) << 8) |
+           (blend_u8(l, (p >> 16) & 255u, alpha, clip) << 16);
+}
+
+// ------------------------------------------------------------ image context --
+struct Ctx {
+    const uint8_t* raw;      // this image, uint8 HWC
+    int H, W;
+    OpRec op[2];             // the two fused op slots (K_NONE when not applied)
+    Box box[2];              // clipped inclusive Cutout boxes (valid when op[j].kind==K_CUTOUT)
+    const uint8_t* lut[2];   // 3x256 per slot (valid when kind_uses_lut)
+};
+
+FAA_HD uint32_t load_raw(const Ctx& c, int x, int y) {
+    const uint8_t* p = c.raw + ((size_t)y * (size_t)c.W + (size_t)x) * 3u;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+#endif
+}
+
+// pointwise part of op slot j applied to an already fetched pixel at frame coords (x,y)
+FAA_HD uint32_t apply_pointwise(const Ctx& c, int j, uint32_t p, int x, int y) {
+    const OpRec& o = c.op[j];
+    switch (o.kind) {
+    case K_LUT: case K_AUTOCONTRAST: case K_EQUALIZE: case K_BRIGHTNESS: case K_CONTRAST:
+        return apply_lut(c.lut[j], p);
+    case K_COLOR:
+        return color_px(p, bits_to_float(o.a[0]), o.a[1] != 0);
+    case K_CUTOUT: {                                          // augmentations.py:142-143
+        const Box& b = c.box[j];
+        return (x >= b.x0 && x <= b.x1 && y >= b.y0 && y <= b.y1) ? kCutoutRGB : p;
+    }
+    default:
+        return p;
+    }
+}
+
+template <int L> struct Level;
+
+template <> struct Level<0> {
+    static FAA_HD uint32_t at(const Ctx& c, int x, int y) { return load_raw(c, x, y); }
+};
+
+// value of the image after the first L op slots, at (x, y) of that image
+template <int L> struct Level {
+    static FAA_HD uint32_t at(const Ctx& c, int x, int y) {
+        const OpRec& o = c.op[L - 1];
+        switch (o.kind) {
+        case K_AFFINE: {     // Pillow affine_fixed: augmentations.py:17,24,61 (NEAREST, zero fill)
+            int xin = (o.a[2] + o.a[0] * x + o.a[1] * y) >> 16;
+            if ((unsigned)xin >= (unsigned)c.W) return 0u;
+            int yin = (o.a[5] + o.a[3] * x + o.a[4] * y) >> 16;
+            if ((unsigned)yin >= (unsigned)c.H) return 0u;
+            return Level<L - 1>::at(c, xin, yin);
+        }
+        case K_SHIFT: {      // Pillow ImagingScaleAffine with unit scale: augmentations.py:32,40,47,54
+            int xin = x + o.a[0], yin = y + o.a[1];
+            if ((unsigned)xin >= (unsigned)c.W || (unsigned)yin >= (unsigned)c.H) return 0u;
+            return Level<L - 1>::at(c, xin, yin);
+        }
+        case K_SHARPNESS: {  // augmentations.py:112-114: blend(SMOOTH(img), img, v)
+            uint32_t ctr = Level<L - 1>::at(c, x, y);
+            if (x == 0 || y == 0 || x == c.W - 1 || y == c.H - 1) return ctr;   // border copied
+            uint32_t s0 = 4u * (ctr & 255u), s1 = 4u * ((ctr >> 8) & 255u), s2 = 4u * ((ctr >> 16) & 255u);
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    uint32_t q = (dx == 0 && dy == 0) ? ctr : Level<L - 1>::at(c, x + dx, y + dy);
+                    s0 += q & 255u; s1 += (q >> 8) & 255u; s2 += (q >> 16) & 255u;
+                }
+            // [1 1 1;1 5 1;1 1 1]/13 rounded half up == (2S+13)/26
+            s0 = (2u * s0 + 13u) / 26u; s1 = (2u * s1 + 13u) / 26u; s2 = (2u * s2 + 13u) / 26u;
+            float al = bits_to_float(o.a[0]); bool clip = o.a[1] != 0;
+            return blend_u8(s0, ctr & 255u, al, clip) | (blend_u8(s1, (ctr >> 8) & 255u, al, clip) << 8) |
+                   (blend_u8(s2, (ctr >> 16) & 255u, al, clip) << 16);
+        }
+        case K_NONE:
+            return Level<L - 1>::at(c, x, y);
+        default:
+            return apply_pointwise(c, L - 1, Level<L - 1>::at(c, x, y), x, y);
+        }
+    }
+};
+
+// ------------------------------------------------------------------- LUTs --
+// static / blend LUT entries: one (channel-independent) byte function
+FAA_HD uint32_t lut_entry_static(const OpRec& o, uint32_t i, uint32_t mean) {
+    switch (o.kind) {
+    case K_LUT: {            // solarize (augmentations.py:80-82), posterize (:85-94), invert (:68-69)
+        uint32_t v = ((int)i < o.a[0]) ? i : 255u - i;
+        return v & (uint32_t)o.a[1];
+    }
+    case K_BRIGHTNESS:       // augmentations.py:107-109
+        return blend_u8(0u, i, bits_to_float(o.a[0]), o.a[1] != 0);
+    case K_CONTRAST:         // augmentations.py:97-99
+        return blend_u8(mean, i, bits_to_float(o.a[0]), o.a[1] != 0);
+    default:
+        return i;
+    }
+}
+
+// ImageEnhance.Contrast: int(ImageStat.mean + 0.5) == (2*sum + N) / (2*N)
+FAA_HD uint32_t contrast_mean(uint64_t sum_l, uint32_t n) {
+    return (uint32_t)((2ull * sum_l + n) / (2ull * n));
+}
+
+// Per-channel partial summary of 8 histogram bins [8*lane, 8*lane+8): phase A of the
+// two-phase (no shuffle, host-emulatable) histogram LUT build.
+struct HistPart { uint32_t sum; int16_t lo; int16_t hi; uint32_t nnz; };
+
+FAA_HD HistPart hist_part(const uint32_t* h256, int lane) {
+    HistPart p; p.sum = 0; p.lo = 256; p.hi = -1; p.nnz = 0;
+    for (int j = 0; j < 8; ++j) {
+        int i = lane * 8 + j;
+        uint32_t v = h256[i];
+        p.sum += v;
+        if (v) { if (i < p.lo) p.lo = (int16_t)i; p.hi = (int16_t)i; ++p.nnz; }
+    }
+    return p;
+}
+
+// phase B: lane writes its 8 LUT entries of one channel.
+//  AutoContrast: PIL ImageOps.autocontrast(cutoff=0)  (augmentations.py:64-65)
+//  Equalize    : PIL ImageOps.equalize                (augmentations.py:72-73)
+FAA_HD void hist_lut_lane(int kind, const uint32_t* h256, const HistPart* parts32, int lane,
+                          uint32_t n_pixels, uint8_t* lut256) {
+    int lo = 256, hi = -1; uint32_t nnz = 0, before = 0;
+    for (int k = 0; k < 32; ++k) {
+        const HistPart& q = parts32[k];
+        if (q.lo < lo) lo = q.lo;
+        if (q.hi > hi) hi = q.hi;
+        nnz += q.nnz;
+        if (k < lane) before += q.sum;
+    }
+    if (kind == K_AUTOCONTRAST) {
+        if (hi <= lo) { for (int j = 0; j < 8; ++j) lut256[lane * 8 + j] = (uint8_t)(lane * 8 + j); return; }
+        double scale = 255.0 / (double)(hi - lo);
+        double offset = d_mul(-(double)lo, scale);
+        for (int j = 0; j < 8; ++j) {
+            int ix = lane * 8 + j;
+            int t = (int)d_add(d_mul((double)ix, scale), offset);       // Python int(): toward zero
+            lut256[ix] = (uint8_t)(t < 0 ? 0 : t > 255 ? 255 : t);
+        }
+    } else {   // K_EQUALIZE
+        uint32_t step = 0;
+        if (nnz > 1) step = (n_pixels - h256[hi]) / 255u;
+        if (step == 0) { for (int j = 0; j < 8; ++j) lut256[lane * 8 + j] = (uint8_t)(lane * 8 + j); return; }
+        uint32_t n = step / 2u + before;
+        for (int j = 0; j < 8; ++j) {
+            int ix = lane * 8 + j;
+            uint32_t v = n / step;
+            lut256[ix] = (uint8_t)(v > 255u ? 255u : v);                // Image.point clips
+            n += h256[ix];
+        }
+    }
+}
+
+// ------------------------------------------------------------------- tail --
+// RandomCrop(+pad) / HFlip / CutoutDefault index logic of data.py:40-41,235-250 for one
+// output pixel.  Returns false when the output is the zero box (caller writes 0), and sets
+// `inside` false when the source falls in the zero padding (pixel value 0,0,0).
+FAA_HD bool tail_source(const Sample& s, bool use_zero_box, int out_w, int H, int W,
+                        int ox, int oy, int& ax, int& ay, bool& inside) {
+    if (use_zero_box && oy >= s.zero_box[0] && oy < s.zero_box[1] && ox >= s.zero_box[2] && ox < s.zero_box[3])
+        return false;
+    int cx = s.flip ? (out_w - 1 - ox) : ox;
+    ax = cx + s.crop_dx;
+    ay = oy + s.crop_dy;
+    inside = (unsigned)ax < (unsigned)W && (unsigned)ay < (unsigned)H;
+    return true;
+}
+
+// ----------------------------------------------------------------- Philox --
+// Philox4x32-10 (Salmon et al. 2011) - the device-side sampler's generator.
+struct U4 { uint32_t x, y, z, w; };
+
+FAA_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = umulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = umulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+        U4 n; n.x = hi1 ^ ctr.y ^ k0; n.y = lo1; n.z = hi0 ^ ctr.w ^ k1; n.w = lo0;
+        ctr = n; k0 += W0; k1 += W1;
+    }
+    return ctr;
+}
+
+// CutoutAbs rectangle from two uniforms (augmentations.py:130-137; numpy's legacy
+// uniform(low=w, high=1.0) = w + (1.0 - w) * u).  v_px is the side in pixels.
+FAA_HD Box cutout_box(int W, int H, double v_px, double ux, double uy) {
+    double cx = d_add((double)W, d_mul(1.0 - (double)W, ux));
+    double cy = d_add((double)H, d_mul(1.0 - (double)H, uy));
+    double half = v_px / 2.0;
+    double l = d_add(cx, -half), t = d_add(cy, -half);
+    int x0 = (int)(l > 0.0 ? l : 0.0);
+    int y0 = (int)(t > 0.0 ? t : 0.0);
+    double r = d_add((double)x0, v_px), b = d_add((double)y0, v_px);
+    if (r > (double)W) r = (double)W;
+    if (b > (double)H) b = (double)H;
+    Box o; o.x0 = (int16_t)x0; o.y0 = (int16_t)y0; o.x1 = (int16_t)(int)r; o.y1 = (int16_t)(int)b;
+    return o;
+}
+
+struct RngCfg { uint64_t seed; uint64_t first_index; int32_t crop_pad; int32_t hflip; int32_t zero_box_len; int32_t reserved; };
+
+// Device-side sampler: one sample's decisions from counter-based draws.  Same
+// distributions as the reference's draws (data.py:259-261, augmentations.py mirror /
+// Cutout draws, torchvision RandomCrop/HFlip, data.py:239-240), different stream.
+// `ops` = compiled table [n_sub][n_op][2], `probs` = [n_sub][n_op].
+FAA_HD void philox_sample(const RngCfg& r, uint64_t index, const OpRec* ops, const double* probs,
+                          int n_sub, int n_op, int H, int W, int out_h, int out_w,
+                          Sample& s, Box* boxes /* n_op */) {
+    uint32_t k0 = (uint32_t)r.seed, k1 = (uint32_t)(r.seed >> 32);
+    U4 c; c.x = (uint32_t)index; c.y = (uint32_t)(index >> 32); c.z = 0; c.w = 0;
+    U4 b0 = philox4x32_10(c, k0, k1);
+    s.sub = (uint16_t)umulhi32(b0.x, (uint32_t)n_sub);
+    s.flip = (uint8_t)(r.hflip ? (b0.y >> 31) : 0u);                     // torch.rand(1) < 0.5
+    int span = 2 * r.crop_pad + 1;
+    s.crop_dy = (int8_t)(r.crop_pad ? (int)umulhi32(b0.z, (uint32_t)span) - r.crop_pad : 0);
+    s.crop_dx = (int8_t)(r.crop_pad ? (int)umulhi32(b0.w, (uint32_t)span) - r.crop_pad : 0);
+    s.reserved = 0;
+    s.zero_box[0] = s.zero_box[1] = s.zero_box[2] = s.zero_box[3] = 0;
+    if (r.zero_box_len > 0) {                                             // data.py:239-246
+        c.z = 1; U4 b1 = philox4x32_10(c, k0, k1);
+        int cy = (int)umulhi32(b1.x, (uint32_t)out_h), cx = (int)umulhi32(b1.y, (uint32_t)out_w);
+        int half = r.zero_box_len / 2;
+        int ya = cy - half, yb = cy + half, xa = cx - half, xb = cx + half;
+        s.zero_box[0] = (int16_t)(ya < 0 ? 0 : ya > out_h ? out_h : ya);
+        s.zero_box[1] = (int16_t)(yb < 0 ? 0 : yb > out_h ? out_h : yb);
+        s.zero_box[2] = (int16_t)(xa < 0 ? 0 : xa > out_w ? out_w : xa);
+        s.zero_box[3] = (int16_t)(xb < 0 ? 0 : xb > out_w ? out_w : xb);
+    }
+    uint32_t gate = 0, sign = 0;
+    for (int j = 0; j < n_op; ++j) {
+        c.z = 2 + j; U4 bj = philox4x32_10(c, k0, k1);
+        const OpRec* o = ops + ((size_t)s.sub * n_op + j) * 2;
+        double u = (double)bj.x * (1.0 / 4294967296.0);
+        boxes[j].x0 = boxes[j].y0 = 0; boxes[j].x1 = boxes[j].y1 = -1;
+        if (u > probs[(size_t)s.sub * n_op + j]) continue;               // data.py:261
+        gate |= 1u << j;
+        if (o->draw == 1) {                                               // mirror: random() > 0.5
+            if (bj.y >> 31) sign |= 1u << j;
+        } else if (o->draw == 2 && o->kind == K_CUTOUT) {
+            double v; { union { int32_t i[2]; double d; } cv; cv.i[0] = o->a[0]; cv.i[1] = o->a[1]; v = cv.d; }
+            boxes[j] = cutout_box(W, H, v, (double)bj.z * (1.0 / 4294967296.0), (double)bj.w * (1.0 / 4294967296.0));
+        }
+    }
+    s.gate = (uint8_t)gate; s.sign = (uint8_t)sign;
+}
+
+// fast exact division of q by d via a 32-bit reciprocal (valid while q*d < 2^32)
+FAA_HD uint32_t recip32(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
+FAA_HD uint32_t fastdiv(uint32_t q, uint32_t rcp) { return umulhi32(q, rcp); }
+
+}  // namespace faa

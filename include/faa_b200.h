@@ -1,0 +1,178 @@
+/*
+ * faa_b200.h - C ABI of the B200-native Fast AutoAugment augmentation hot path.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status returns, no C++
+ * or torch types, no exceptions across the boundary.  Every device entry point
+ * takes an explicit CUDA stream (passed as void*, i.e. a cudaStream_t) and is
+ * asynchronous with respect to the host; the caller owns every device buffer,
+ * the library owns only the policy handle and its small device-side tables.
+ *
+ * The reference (kakaobrain/fast-autoaugment @ 2424224) has no FFI: its
+ * boundary for this path is a set of Python callables.  Each entry point below
+ * names the reference interface it replaces (file:line relative to the
+ * reference root).  The Python mirror of that surface lives in
+ * fast_autoaugment_b200/ and binds this header with ctypes; INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ */
+#ifndef FAA_B200_H
+#define FAA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAA_ABI_VERSION 1
+#define FAA_MAX_FUSED_OPS 2      /* ops of one sub-policy applied by one launch */
+#define FAA_MAX_POLICY_OPS 8     /* ops per sub-policy (search.py --num-op); >2 runs as chained launches */
+#define FAA_MAX_DIM 8192         /* max H or W */
+
+/* status codes; the Python layer maps them to the reference's exceptions */
+enum faa_status {
+    FAA_OK = 0,
+    FAA_ERR_UNKNOWN_OP = 1,   /* KeyError      - augmentations.py:189 get_augment */
+    FAA_ERR_MAGNITUDE = 2,    /* AssertionError- augmentations.py:14,21,28,36,44,51,58,81,86,92,98,103,108,113,118 */
+    FAA_ERR_VALUE = 3,        /* ValueError    - bad argument */
+    FAA_ERR_CUDA = 4,         /* RuntimeError  - CUDA runtime error, see faa_last_error() */
+    FAA_ERR_NO_DEVICE = 5,    /* RuntimeError  - no CUDA device: there is NO CPU fallback */
+    FAA_ERR_UNSUPPORTED = 6   /* RuntimeError  - shape / option outside what the kernels handle */
+};
+
+/* op ids = position in augment_list(for_autoaug=True), augmentations.py:156-182 */
+enum faa_op_id {
+    FAA_SHEAR_X = 0, FAA_SHEAR_Y = 1, FAA_TRANSLATE_X = 2, FAA_TRANSLATE_Y = 3, FAA_ROTATE = 4,
+    FAA_AUTOCONTRAST = 5, FAA_INVERT = 6, FAA_EQUALIZE = 7, FAA_SOLARIZE = 8, FAA_POSTERIZE = 9,
+    FAA_CONTRAST = 10, FAA_COLOR = 11, FAA_BRIGHTNESS = 12, FAA_SHARPNESS = 13, FAA_CUTOUT = 14,
+    FAA_CUTOUT_ABS = 15, FAA_POSTERIZE2 = 16, FAA_TRANSLATE_X_ABS = 17, FAA_TRANSLATE_Y_ABS = 18,
+    FAA_NUM_OPS = 19
+};
+
+/* which random draws an applied op consumes (augmentations.py:15,22,29,37,45,52,59,131-132) */
+enum faa_draw { FAA_DRAW_NONE = 0, FAA_DRAW_MIRROR = 1, FAA_DRAW_BOX = 2 };
+
+enum faa_dtype { FAA_F16 = 0, FAA_BF16 = 1, FAA_F32 = 2, FAA_U8_HWC = 3 };
+
+/*
+ * Per-sample resolved decisions: what the reference's RNG draws decided for one
+ * image (data.py:257-264 Augmentation.__call__, torchvision RandomCrop /
+ * RandomHorizontalFlip data.py:40-41, CutoutDefault data.py:235-244).
+ * Filled on the host by the parity sampler or on the device by the Philox one.
+ */
+typedef struct faa_sample {
+    uint16_t sub;          /* chosen sub-policy (random.choice, data.py:259)              */
+    uint8_t  gate;         /* bit j: op j passed its `random.random() > pr` gate (:261)    */
+    uint8_t  sign;         /* bit j: op j drew the mirrored (-v) variant                   */
+    int8_t   crop_dy;      /* RandomCrop: top  - padding  (source row = out row + crop_dy) */
+    int8_t   crop_dx;      /* RandomCrop: left - padding                                   */
+    uint8_t  flip;         /* RandomHorizontalFlip fired                                   */
+    uint8_t  reserved;
+    int16_t  zero_box[4];  /* CutoutDefault half-open, clipped: y1, y2, x1, x2 (data.py:241-246) */
+} faa_sample_t;            /* 16 bytes */
+
+/* per-sample, per-op inclusive Cutout rectangle x0, y0, x1, y1 (augmentations.py:134-143),
+ * already truncated to integers, NOT yet clipped to the image */
+typedef struct faa_box { int16_t x0, y0, x1, y1; } faa_box_t;
+
+/* the part of the train chain behind the policy (data.py:39-44, 64, 70-72, 111-112) */
+typedef struct faa_tail {
+    int32_t out_h, out_w;     /* RandomCrop size (== H, W when there is no crop)            */
+    int32_t out_dtype;        /* enum faa_dtype; FAA_U8_HWC skips ToTensor/Normalize         */
+    int32_t use_zero_box;     /* apply faa_sample.zero_box (CutoutDefault)                   */
+    float   mean[3], std[3];  /* Normalize                                                  */
+} faa_tail_t;
+
+/* parameters of the device-side (Philox4x32-10) sampler: the distribution of every draw
+ * is the reference's, the stream is not (statistical equivalence, not replay) */
+typedef struct faa_rng {
+    uint64_t seed;            /* key                                                        */
+    uint64_t first_index;     /* global index of sample 0 of this call (shard offset)        */
+    int32_t  crop_pad;        /* RandomCrop padding (0 = no crop)                            */
+    int32_t  hflip;           /* RandomHorizontalFlip present                                */
+    int32_t  zero_box_len;    /* CutoutDefault length (0 = off)                              */
+    int32_t  reserved;
+} faa_rng_t;
+
+typedef struct faa_policy faa_policy_t;
+
+/* ---- misc ------------------------------------------------------------------ */
+int         faa_abi_version(void);
+const char* faa_last_error(void);          /* thread-local message of the last failing call */
+int         faa_device_count(void);        /* 0 when no usable CUDA device */
+int         faa_op_id_from_name(const char* name);   /* -1 if unknown; names of augment_list() */
+const char* faa_op_name(int op_id);
+int         faa_op_range(int op_id, double* low, double* high);   /* augmentations.py:157-181 */
+
+/* ---- policy: replaces Augmentation.__init__ (data.py:254-255) over the archive.py
+ *      list-of-sub-policies format.  ops/probs/levels are row-major [n_sub][n_op].
+ *      Magnitudes are range-checked here (the reference asserts per call).        */
+int faa_policy_create(const int32_t* op_ids, const double* probs, const double* levels,
+                      int n_sub, int n_op, faa_policy_t** out);
+int faa_policy_destroy(faa_policy_t* p);
+int faa_policy_dims(const faa_policy_t* p, int* n_sub, int* n_op);
+/* host-side compiled op record (32 bytes) for (sub, op, sign) at image size (h, w):
+ * exposes the level->magnitude->fixed-point compilation (augmentations.py:192-194 + Pillow
+ * matrix set-up) for tests and foreign hosts.  No GPU needed. */
+int faa_policy_compiled_op(faa_policy_t* p, int h, int w, int sub, int op, int sign, int32_t out8[8]);
+int faa_policy_draw_kind(const faa_policy_t* p, int sub, int op);     /* enum faa_draw */
+/* CutoutAbs box from the two uniforms (augmentations.py:131-137), host helper */
+int faa_cutout_box(const faa_policy_t* p, int h, int w, int sub, int op, double ux, double uy,
+                   faa_box_t* out);
+
+/* ---- host parity sampler: replays Augmentation.__call__'s draws (data.py:257-264) for
+ *      `batch` images drawn one after another, from explicit MT19937 states of Python's
+ *      `random` (624 words + index) and numpy's legacy global RandomState (same layout).
+ *      States are advanced in place.  Tail draws (torch generator) are not covered here. */
+int faa_sample_policy_mt(const faa_policy_t* p, int batch, int h, int w,
+                         uint32_t py_state[625], uint32_t np_state[625],
+                         faa_sample_t* out_samples, faa_box_t* out_boxes /* [batch][n_op] */);
+
+/* ---- device sampler (Philox): fills samples/boxes on the device -------------- */
+int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t* tail,
+                      const faa_rng_t* rng, faa_sample_t* d_samples, faa_box_t* d_boxes,
+                      void* stream);
+
+/* ---- the hot path: replaces, for a whole batch, Augmentation.__call__ (data.py:257-264)
+ *      -> apply_augment (augmentations.py:192-194) -> the 19 ops (augmentations.py:13-144)
+ *      -> RandomCrop/HFlip/ToTensor/Normalize (data.py:40-43, 64, 70-72)
+ *      -> CutoutDefault (data.py:235-250).
+ *      d_in : uint8 [batch][h][w][3] (HWC, contiguous) on the device
+ *      d_out: [batch][3][out_h][out_w] of tail->out_dtype (or uint8 HWC)
+ *      d_samples / d_boxes: resolved decisions; if d_samples == NULL the kernel draws them
+ *      itself from `rng` (fused Philox mode).  op_base selects which FAA_MAX_FUSED_OPS-wide
+ *      window of the sub-policy this launch applies (chained launches for n_op > 2). */
+int faa_augment(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, int h, int w,
+                const faa_tail_t* tail, const faa_sample_t* d_samples, const faa_box_t* d_boxes,
+                const faa_rng_t* rng, int op_base, void* stream);
+
+/* fused Mixup variant: out[i] = lam*aug(in[i]) + one_minus_lam*aug(in[partner[i]]) in fp32
+ * (lam and one_minus_lam are the fp32 casts of the Python floats lam and 1-lam)
+ * (aug_mixup.py:13-23 with the pairing resolved by the caller; partner indexes d_in_all,
+ * which may be an all-gathered or peer-mapped array of n_all images with its own
+ * samples/boxes).  d_partner == NULL or lam == 1 degenerates to faa_augment. */
+int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out,
+                      int batch, int h, int w, const faa_tail_t* tail,
+                      const faa_sample_t* d_samples_all, const faa_box_t* d_boxes_all,
+                      const faa_rng_t* rng, const int32_t* d_partner, float lam, float one_minus_lam,
+                      void* stream);
+
+/* same call with HOST buffers: pinned staging, chunked H2D / kernel / D2H pipeline inside.
+ * h_out may be NULL (result stays on the device in d_out_keep, which may also be NULL). */
+int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_out_keep,
+                     int batch, int h, int w, const faa_tail_t* tail, const faa_rng_t* rng,
+                     void* stream);
+
+/* ---- standalone Mixup on already-augmented device tensors: replaces mixup()
+ *      (aug_mixup.py:13-23) given the resolved permutation and lambda.
+ *      out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math, n_per_sample elements each. */
+int faa_mixup(const void* d_data, void* d_out, const int64_t* d_perm, int batch,
+              int64_t n_per_sample, int dtype, float lam, float one_minus_lam, void* stream);
+
+/* number of kernels this library has launched since load (bench bookkeeping) */
+uint64_t faa_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAA_B200_H */

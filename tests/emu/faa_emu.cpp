@@ -1,0 +1,215 @@
+// faa_emu.cpp - HOST emulation of the CUDA kernels' control flow, TEST INFRASTRUCTURE ONLY.
+//
+// There is no GPU in the build container, so the CPU test-suite cannot run the kernels.
+// This file compiles the very same per-pixel arithmetic header the kernels use
+// (fast_autoaugment_b200/csrc/faa_core.cuh: lazy op-chain evaluation, LUT builders, blend,
+// tail index map, Philox sampler) with g++ and drives it with the kernel's control flow
+// for ONE band per image (cluster size 1), so the arithmetic the GPU will execute is
+// checked against the oracle on the CPU first.  It is not part of the product: the
+// package never loads it, and the product has no CPU fallback.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../fast_autoaugment_b200/csrc/faa_core.cuh"
+
+using namespace faa;
+
+namespace {
+
+struct State {
+    uint32_t hist[2][768];
+    uint32_t tot[768];
+    uint8_t lut[2][768];
+    HistPart parts[3][32];
+    unsigned long long suml[2];
+    Sample smp;
+    Box box[2];
+    OpRec op[2];
+};
+
+void load_program(const OpRec* ops, int n_op, int op_base, int apply_tail, int H, int W, const Sample& in_s,
+                  const Box* in_boxes, State& st) {
+    Sample s = in_s;
+    if (!apply_tail) { s.crop_dx = s.crop_dy = 0; s.flip = 0; }
+    st.smp = s;
+    for (int j = 0; j < 2; ++j) {
+        int jj = op_base + j;
+        OpRec o; memset(&o, 0, sizeof o); o.kind = K_NONE;
+        if (jj < n_op && ((s.gate >> jj) & 1u)) o = ops[((size_t)s.sub * n_op + jj) * 2 + ((s.sign >> jj) & 1u)];
+        st.op[j] = o;
+        Box b; b.x0 = b.y0 = 0; b.x1 = b.y1 = -1;
+        if (o.kind == K_CUTOUT) {
+            b = in_boxes[jj];
+            if (b.x0 < 0) b.x0 = 0;
+            if (b.y0 < 0) b.y0 = 0;
+            if (b.x1 > W - 1) b.x1 = (int16_t)(W - 1);
+            if (b.y1 > H - 1) b.y1 = (int16_t)(H - 1);
+        }
+        st.box[j] = b;
+        st.suml[j] = 0;
+    }
+    memset(st.hist, 0, sizeof st.hist);
+}
+
+Ctx make_ctx(const uint8_t* raw, int H, int W, const State& st) {
+    Ctx c; c.raw = raw; c.H = H; c.W = W;
+    c.op[0] = st.op[0]; c.op[1] = st.op[1]; c.box[0] = st.box[0]; c.box[1] = st.box[1];
+    c.lut[0] = st.lut[0]; c.lut[1] = st.lut[1];
+    return c;
+}
+
+template <int L>
+void accumulate(const Ctx& c, int kind, uint32_t* hist, unsigned long long* suml) {
+    for (int y = 0; y < c.H; ++y)
+        for (int x = 0; x < c.W; ++x) {
+            uint32_t p = Level<L>::at(c, x, y);
+            if (kind == K_CONTRAST) *suml += luma_of(p);
+            else { hist[p & 255u]++; hist[256 + ((p >> 8) & 255u)]++; hist[512 + (p >> 16)]++; }
+        }
+}
+
+void build_lut(State& st, int j, int H, int W) {
+    const int kind = st.op[j].kind;
+    uint32_t mean = 0;
+    if (kind_needs_hist(kind)) memcpy(st.tot, st.hist[j], sizeof st.tot);
+    if (kind_needs_mean(kind)) mean = contrast_mean(st.suml[j], (uint32_t)H * (uint32_t)W);
+    if (kind_needs_hist(kind)) {
+        for (int t = 0; t < 96; ++t) st.parts[t >> 5][t & 31] = hist_part(&st.tot[(t >> 5) * 256], t & 31);
+        for (int t = 0; t < 96; ++t)
+            hist_lut_lane(kind, &st.tot[(t >> 5) * 256], st.parts[t >> 5], t & 31, (uint32_t)H * (uint32_t)W,
+                          &st.lut[j][(t >> 5) * 256]);
+    } else if (kind_uses_lut(kind)) {
+        for (int i = 0; i < 768; ++i) st.lut[j][i] = (uint8_t)lut_entry_static(st.op[j], (uint32_t)(i & 255), mean);
+    }
+}
+
+void prepare(const uint8_t* raw, int H, int W, State& st) {
+    for (int j = 0; j < 2; ++j) {
+        int kind = st.op[j].kind;
+        if (kind_needs_hist(kind) || kind_needs_mean(kind)) {
+            Ctx c = make_ctx(raw, H, W, st);
+            if (j == 0) accumulate<0>(c, kind, st.hist[0], &st.suml[0]);
+            else accumulate<1>(c, kind, st.hist[1], &st.suml[1]);
+        }
+        if (kind_uses_lut(kind)) build_lut(st, j, H, W);
+    }
+}
+
+// the kernel's fast path (pointwise-only program, aligned quads): emulated too, so both
+// code paths are checked
+void quad_pixels(const Ctx& c, const Sample& s, bool fast, bool use_zero_box, int out_w, int ox0, int oy,
+                 uint32_t px[4], uint32_t& zmask) {
+    zmask = 0;
+    if (fast) {
+        const int sx0 = (s.flip ? (out_w - 4 - ox0) : ox0) + s.crop_dx;
+        const int ay = oy + s.crop_dy;
+        uint32_t q[4] = {0, 0, 0, 0};
+        const bool inside = (unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H;
+        if (inside) {
+            const uint8_t* b = c.raw + ((size_t)ay * c.W + sx0) * 3u;
+            uint32_t w[3]; memcpy(w, b, 12);
+            q[0] = w[0] & 0xFFFFFFu;
+            q[1] = (w[0] >> 24) | ((w[1] & 0xFFFFu) << 8);
+            q[2] = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
+            q[3] = w[2] >> 8;
+            for (int k = 0; k < 4; ++k)
+                q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+        }
+        for (int k = 0; k < 4; ++k) {
+            px[k] = s.flip ? q[3 - k] : q[k];
+            const int ox = ox0 + k;
+            if (use_zero_box && oy >= s.zero_box[0] && oy < s.zero_box[1] && ox >= s.zero_box[2] && ox < s.zero_box[3])
+                zmask |= 1u << k;
+        }
+        return;
+    }
+    for (int k = 0; k < 4; ++k) {
+        const int ox = ox0 + k;
+        px[k] = 0u;
+        if (ox >= out_w) continue;
+        int ax, ay; bool inside;
+        if (!tail_source(s, use_zero_box, out_w, c.H, c.W, ox, oy, ax, ay, inside)) { zmask |= 1u << k; continue; }
+        if (inside) px[k] = Level<2>::at(c, ax, ay);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ops: compiled table [n_sub][n_op][2] (32-byte records); samples/boxes indexed like the kernel's.
+// norm_tab == NULL -> uint8 HWC output, else fp32 NCHW through the exact table.
+// force_generic != 0 disables the aligned fast path (to test both).
+int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W, const void* ops_v, int n_sub,
+                    int n_op, const void* samples_v, const void* boxes_v, int op_base, int apply_tail, int out_h,
+                    int out_w, int use_zero_box, const float* norm_tab, void* out, const int32_t* partner,
+                    float lam, float oml, int force_generic) {
+    (void)n_sub; (void)n_all;
+    const OpRec* ops = (const OpRec*)ops_v;
+    const Sample* samples = (const Sample*)samples_v;
+    const Box* boxes = (const Box*)boxes_v;
+    const int nsrc = partner ? 2 : 1;
+    std::vector<State> st(2);
+    const size_t img_bytes = (size_t)H * W * 3;
+    for (int img = 0; img < B; ++img) {
+        int src[2] = {first + img, partner ? partner[img] : 0};
+        Ctx c[2]; Sample s[2]; bool fast[2];
+        const bool geom_ok = ((W & 3) == 0) && ((out_w & 3) == 0) && !force_generic;
+        for (int k = 0; k < nsrc; ++k) {
+            load_program(ops, n_op, op_base, apply_tail, H, W, samples[src[k]], boxes + (size_t)src[k] * n_op, st[k]);
+            prepare(in + img_bytes * src[k], H, W, st[k]);
+            c[k] = make_ctx(in + img_bytes * src[k], H, W, st[k]);
+            s[k] = st[k].smp;
+            fast[k] = geom_ok && kind_is_pointwise(c[k].op[0].kind) && kind_is_pointwise(c[k].op[1].kind) &&
+                      ((s[k].crop_dx & 3) == 0);
+        }
+        const bool zb = use_zero_box && apply_tail;
+        for (int oy = 0; oy < out_h; ++oy)
+            for (int ox0 = 0; ox0 < out_w; ox0 += 4) {
+                uint32_t px[2][4], zm[2] = {0, 0};
+                for (int k = 0; k < nsrc; ++k) quad_pixels(c[k], s[k], fast[k], zb, out_w, ox0, oy, px[k], zm[k]);
+                const int nvalid = (out_w - ox0) < 4 ? (out_w - ox0) : 4;
+                for (int k = 0; k < nvalid; ++k) {
+                    if (!norm_tab) {
+                        uint32_t p = ((zm[0] >> k) & 1u) ? 0u : px[0][k];
+                        uint8_t* o = (uint8_t*)out + (((size_t)img * out_h + oy) * out_w + ox0 + k) * 3;
+                        o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
+                    } else {
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float a = ((zm[0] >> k) & 1u) ? 0.0f : norm_tab[ch * 256 + ((px[0][k] >> (8 * ch)) & 255u)];
+                            if (nsrc == 2) {
+                                float b = ((zm[1] >> k) & 1u) ? 0.0f : norm_tab[ch * 256 + ((px[1][k] >> (8 * ch)) & 255u)];
+                                a = f_add(f_mul(a, lam), f_mul(b, oml));
+                            }
+                            ((float*)out)[(((size_t)img * 3 + ch) * out_h + oy) * out_w + ox0 + k] = a;
+                        }
+                    }
+                }
+            }
+    }
+    return 0;
+}
+
+int faa_emu_philox(const void* ops_v, const double* probs, int n_sub, int n_op, const void* rng_v, int B, int H,
+                   int W, int out_h, int out_w, void* samples_v, void* boxes_v) {
+    const OpRec* ops = (const OpRec*)ops_v;
+    RngCfg r; memcpy(&r, rng_v, sizeof r);
+    Sample* samples = (Sample*)samples_v;
+    Box* boxes = (Box*)boxes_v;
+    for (int i = 0; i < B; ++i) {
+        Box bx[8];
+        philox_sample(r, r.first_index + (uint64_t)i, ops, probs, n_sub, n_op, H, W, out_h, out_w, samples[i], bx);
+        for (int j = 0; j < n_op; ++j) boxes[(size_t)i * n_op + j] = bx[j];
+    }
+    return 0;
+}
+
+// raw Philox4x32-10 block, for the known-answer test
+void faa_emu_philox_block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    U4 c; c.x = ctr[0]; c.y = ctr[1]; c.z = ctr[2]; c.w = ctr[3];
+    U4 r = philox4x32_10(c, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+}  // extern "C"
