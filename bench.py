@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py - augmented images/sec of the Fast AutoAugment hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 via torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU PIL path, rank 0 only)
+
+A "step" is one pass of the hot path over one batch of synthetic uint8 HWC images:
+policy ops -> HFlip -> ToTensor -> Normalize -> NCHW fp16, with the per-sample decisions
+drawn by the fused Philox sampler.  Workload = BASELINE.json configs[2] (the configuration the
+metric is quoted on): 224x224, batch 512 per GPU, fa_reduced_imagenet policy.  Weak scaling:
+every rank processes its own 512-image shard, no data-path collective (images are
+independent).
+
+The JSON line carries the device-timed `value`, the host-buffer `e2e`, the HBM `roofline`
+of the fused kernel (algorithmic bytes 9*H*W per image / measured launch time / measured
+copy peak) and the CPU `cpu_baseline` (the reference's PIL/torchvision call sequence as
+restated in oracle/pil_path.py, run through a torch DataLoader like reference data.py:214).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, per-GPU batch, policy fn name, tail kind, cutout)
+    "imagenet224_b512": (224, 224, 512, "fa_resnet50_rimagenet", "imagenet", 0),
+    "cifar32_b512": (32, 32, 512, "fa_reduced_cifar10", "cifar", 16),
+    "effnetb4_380_b256": (380, 380, 256, "fa_resnet50_rimagenet", "imagenet", 16),
+}
+METRIC = "augmented images/sec at 224x224 b512 (1/2/4/8 GPU) + % HBM roofline vs CPU PIL"
+
+
+def synth_batch(n, h, w, seed):
+    """SURVEY.md 8(d) input families, interleaved: uniform noise / low-contrast ramp+noise /
+    constant colour (histogram worst case)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, h, w, 3), np.uint8)
+    for i in range(n):
+        k = i % 3
+        if k == 0:
+            out[i] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif k == 1:
+            lo = int(rng.integers(0, 200))
+            hi = int(rng.integers(lo + 1, 256))
+            ramp = np.linspace(lo, hi, w)[None, :, None] + rng.normal(0, 8, (h, w, 3))
+            out[i] = np.clip(ramp, 0, 255).astype(np.uint8)
+        else:
+            out[i] = rng.integers(0, 256, 3, dtype=np.uint8)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the reference's per-sample PIL chain inside a torch DataLoader
+class _ArrayDataset:
+    def __init__(self, arrays, n_total, chain):
+        self.arrays, self.n_total, self.chain = arrays, n_total, chain
+
+    def __len__(self):
+        return self.n_total
+
+    def __getitem__(self, i):
+        import PIL.Image
+        return self.chain(PIL.Image.fromarray(self.arrays[i % len(self.arrays)])), 0
+
+
+def _cpu_chain(workload):
+    from fast_autoaugment_b200 import archive
+    from oracle import pil_path
+    h, w, b, pol_name, tail_kind, cutout = WORKLOADS[workload]
+    policies = getattr(archive, pol_name)()
+    if tail_kind == "cifar":
+        return pil_path.cifar_train_chain(policies, cutout)
+    return pil_path.fixed_shape_chain(policies, pil_path.IMAGENET_MEAN, pil_path.IMAGENET_STD, True, cutout)
+
+
+def cpu_throughput(workload, n_batches, warm_batches, workers):
+    """images/s of the reference CPU path over `n_batches` batches after `warm_batches`
+    (worker start-up excluded, reference-style DataLoader: data.py:214-216)."""
+    import torch
+    from torch.utils.data import DataLoader
+    h, w, b, *_ = WORKLOADS[workload]
+    arrays = synth_batch(min(b, 256), h, w, 1234)
+    # Worker task = b/workers images instead of the reference's whole batch per worker: the
+    # steady-state rate is the same (workers x per-core rate) but a step (= b images) is then
+    # one even round over all workers, so a short timed region is not distorted by whole
+    # batches that were prefetched before the clock started.
+    task = max(1, b // max(1, workers))
+    tasks_per_step = (b + task - 1) // task
+    warm_batches = max(warm_batches, 3)          # >= prefetch depth (2 tasks per worker)
+    ds = _ArrayDataset(arrays, task * tasks_per_step * (n_batches + warm_batches), _cpu_chain(workload))
+    torch.set_num_threads(1)
+    dl = DataLoader(ds, batch_size=task, shuffle=False, num_workers=workers, drop_last=True,
+                    persistent_workers=False, prefetch_factor=(2 if workers > 0 else None))
+    it = iter(dl)
+    for _ in range(warm_batches * tasks_per_step):
+        next(it)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(n_batches * tasks_per_step):
+        x, _ = next(it)
+        n += x.shape[0]
+    dt = time.perf_counter() - t0
+    del it
+    return n / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:       # region shorter than the sampling period: take every sample we have
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        sm.sort()
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """per-launch DRAM bytes of the fused kernel from the committed ncu capture, if any"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fast_autoaugment_b200 import _lib, archive
+    from fast_autoaugment_b200.engine import CompiledPolicy, FusedAugmenter, TailSpec, make_rng
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    H, W, B, pol_name, tail_kind, cutout = WORKLOADS[args.workload]
+    pol = CompiledPolicy(getattr(archive, pol_name)())
+    tail = TailSpec.cifar(cutout, torch.float16) if tail_kind == "cifar" else TailSpec.imagenet(cutout, torch.float16)
+    t_c = tail.c_struct(H, W)
+    out_shape = (B, 3, t_c.out_h, t_c.out_w)
+
+    # inputs resident in HBM; NSETS buffer sets rotate so no step finds its data in L2
+    NSETS = 4
+    host_in = torch.from_numpy(synth_batch(B, H, W, 1234 + rank)).pin_memory()
+    ins = [host_in.cuda().clone() for _ in range(NSETS)]
+    outs = [torch.empty(out_shape, dtype=torch.float16, device="cuda") for _ in range(NSETS)]
+    in_bytes, out_bytes = B * H * W * 3, B * 3 * t_c.out_h * t_c.out_w * 2
+    set_bytes = in_bytes + out_bytes
+    stream = torch.cuda.current_stream()
+
+    fused = FusedAugmenter(pol, tail, H, W, args.seed)
+    raw_stream = stream.cuda_stream
+
+    def step(i):
+        fused(ins[i % NSETS], outs[i % NSETS], (i * world + rank) * B, raw_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    # ---- device-timed region: exactly K steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.lib.faa_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    launches = int(_lib.lib.faa_launch_count() - launches0)
+    ms = ev0.elapsed_time(ev1)
+    # keep the GPU busy a little longer if the region was too short for a clock sample
+    if t1 - t0 < 0.4:
+        tb = time.perf_counter()
+        j = 0
+        while time.perf_counter() - tb < 0.5:
+            step(j)
+            j += 1
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+    clk = clocks.stop(t0, t1)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernel + D2H per step
+    host_out = torch.empty(out_shape, dtype=torch.float16).pin_memory()
+    keep = torch.empty(out_shape, dtype=torch.float16, device="cuda")
+
+    def e2e_step(i, back):
+        rng = make_rng(args.seed, (i * world + rank) * B, tail)
+        _lib.check(_lib.lib.faa_augment_host(pol.handle, host_in.data_ptr(), host_out.data_ptr() if back else None,
+                                             keep.data_ptr(), B, H, W, C.byref(t_c), C.byref(rng),
+                                             C.c_void_p(stream.cuda_stream)))
+
+    e2e = {}
+    for name, back in (("roundtrip", True), ("device_out", False)):
+        for i in range(max(3, args.warmup)):
+            e2e_step(i, back)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            e2e_step(i, back)
+            if not back:                       # the consumer reads one scalar of the result
+                _ = keep[0, 0, 0, 0].item()
+        e1.record(stream)
+        barrier()
+        e2e[name] = e0.elapsed_time(e1)
+
+    # ---- max over ranks
+    vals = torch.tensor([ms, e2e["roundtrip"], e2e["device_out"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms, ms_rt, ms_dev = (float(v) for v in vals.tolist())
+
+    if rank == 0:
+        total = world * B * args.steps
+        value = total / (ms / 1e3)
+        peak, peak_src = measured_peak()
+        alg_bytes = 9 * H * W * B if (t_c.out_h, t_c.out_w) == (H, W) else in_bytes + out_bytes
+        achieved = alg_bytes / (ms / args.steps / 1e3) / 1e9          # per rank: one launch per step
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "%s: uint8 HWC %dx%d, batch %d per GPU, %s policy, HFlip+ToTensor+Normalize%s, "
+                                   "NCHW fp16 out, fused Philox sampler" % (args.workload, H, W, B, pol_name,
+                                                                            "+CutoutDefault(%d)" % cutout if cutout else ""),
+                       "global_batch": world * B, "parallelism": "dp%d (independent shards, no collective)" % world,
+                       "l2": "inputs/outputs rotate over %d buffer sets (%.0f MB) > 126 MB L2" % (NSETS, NSETS * set_bytes / 1e6)},
+            "clocks": clk,
+            "e2e": {"value": total / (ms_rt / 1e3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes,
+                    "what": "faa_augment_host: pinned host uint8 in -> pinned host fp16 out (chunked H2D/kernel/D2H pipeline)"},
+            "e2e_device_out": {"value": total / (ms_dev / 1e3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                               "d2h_bytes_per_step": 2,
+                               "what": "same call, result left on the device for the model (train.py:49 becomes a no-op); one scalar read back"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "faa_augment_kernel<f16,1>"},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = host_cores()
+            workers = min(8, cores)
+            nb = 24 if H >= 224 else 80
+            v, dt = cpu_throughput(args.workload, nb, 2, workers)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": workers, "kind": "port",
+                                    "host_cores": cores,
+                                    "sample": "%d batches of %d through the reference's PIL/torchvision call sequence "
+                                              "(oracle/pil_path.py) in a torch DataLoader with %d workers "
+                                              "(reference data.py:215), first 2 batches excluded; %.1f s" % (nb, B, workers, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (the oracle port of
+    its PIL/torchvision call sequence - the reference is pure Python, nothing to compile),
+    DataLoader with every host core as a worker.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    H, W, B, *_ = WORKLOADS[args.workload]
+    cores = host_cores()
+    workers = max(1, cores)
+    steps = max(1, args.steps)
+    warm = max(1, args.warmup)
+    v, dt = cpu_throughput(args.workload, steps, warm, workers)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))), "steps": steps, "warmup": warm,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%s: uint8 HWC %dx%d, batch %d, CPU PIL/torchvision chain -> fp32 NCHW" % (args.workload, H, W, B),
+                   "global_batch": B, "parallelism": "torch DataLoader, %d worker processes" % workers},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": workers, "kind": "port",
+                         "sample": "%d steps of one %d-image batch each, %d DataLoader workers, %d warm-up batches excluded" % (steps, B, workers, warm)},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="imagenet224_b512", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:      # convenience: self-launch under torchrun
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,20 +69,31 @@ static double py_fmod(double a, double b) {
     if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
     return r;
 }
-// ImagingScaleAffine axis table with accumulation (Geometry.c); returns the integer shift
-// or INT32_MIN when the mapping is not a pure shift
-static int32_t unit_scale_shift(int n, double scale, double offset) {
-    double o = offset + scale * 0.5;
-    bool have = false; int32_t shift = 0;
+// ImagingScaleAffine axis table (Geometry.c): o = offset + scale*0.5, then o += scale per
+// pixel, COORD(o) = o < 0 ? -1 : (int)o.  With unit scale the table is "i + shift", except
+// that the repeatedly rounded accumulator may snap up to the next integer once (when
+// offset+0.5 sits a few ulp below an integer): from index `brk` on the shift is shift+1.
+// Returns false when the table is anything else.
+static bool unit_scale_shift(int n, double offset, int32_t* shift, int32_t* brk) {
+    double o = offset + 0.5;
+    bool have = false; int32_t sh = 0, bk = INT32_MAX;
+    std::vector<int32_t> tab(n);
+    for (int i = 0; i < n; ++i) { tab[i] = (o < 0.0) ? INT32_MIN : (int32_t)o; o += 1.0; }
     for (int i = 0; i < n; ++i) {
-        int c = (o < 0.0) ? -1 : (int)o;
-        if (c >= 0 && c < n) {
-            if (!have) { shift = c - i; have = true; }
-            else if (c - i != shift) return INT32_MIN;
-        }
-        o += scale;
+        if (tab[i] == INT32_MIN) continue;
+        int32_t d = tab[i] - i;
+        if (!have) { sh = d; have = true; }
+        else if (d == sh + 1 && bk == INT32_MAX) bk = i;
+        else if (d != sh + (bk != INT32_MAX ? 1 : 0)) return false;
     }
-    return have ? shift : (int32_t)FAA_MAX_DIM * 2;     // nothing maps inside: everything is fill
+    if (!have) { *shift = -2 * (int32_t)FAA_MAX_DIM; *brk = INT32_MAX; return true; }   // everything is fill
+    for (int i = 0; i < n; ++i) {            // negative accumulator => Pillow skips the pixel
+        if (tab[i] != INT32_MIN) continue;
+        int32_t c = i + sh + (i >= bk ? 1 : 0);
+        if (c >= 0 && c < n) return false;
+    }
+    *shift = sh; *brk = bk;
+    return true;
 }
 
 struct Compiled { OpRec rec; int err; };   // err: 0 ok, FAA_ERR_UNKNOWN_OP, FAA_ERR_MAGNITUDE, FAA_ERR_UNSUPPORTED
@@ -90,10 +101,10 @@ struct Compiled { OpRec rec; int err; };   // err: 0 ok, FAA_ERR_UNKNOWN_OP, FAA
 static void set_affine(OpRec& r, const double m[6], int H, int W, int& err) {
     if (m[1] == 0.0 && m[3] == 0.0) {                     // Pillow: pure scale -> ImagingScaleAffine
         if (m[0] != 1.0 || m[4] != 1.0) { err = FAA_ERR_UNSUPPORTED; return; }
-        int32_t dx = unit_scale_shift(W, 1.0, m[2]), dy = unit_scale_shift(H, 1.0, m[5]);
-        if (dx == INT32_MIN || dy == INT32_MIN) { err = FAA_ERR_UNSUPPORTED; return; }
-        if (dx == 0 && dy == 0) { r.kind = K_NONE; return; }
-        r.kind = K_SHIFT; r.a[0] = dx; r.a[1] = dy;
+        int32_t dx, dy, bx, by;
+        if (!unit_scale_shift(W, m[2], &dx, &bx) || !unit_scale_shift(H, m[5], &dy, &by)) { err = FAA_ERR_UNSUPPORTED; return; }
+        if (dx == 0 && dy == 0 && bx == INT32_MAX && by == INT32_MAX) { r.kind = K_NONE; return; }
+        r.kind = K_SHIFT; r.a[0] = dx; r.a[1] = dy; r.a[2] = bx; r.a[3] = by;
         return;
     }
     r.kind = K_AFFINE;                                    // Pillow affine_fixed

@@ -28,7 +28,9 @@ namespace faa {
 enum Kind : int32_t {
     K_NONE = 0,          // identity (gate not passed, Rotate by 0, Cutout with v<=0 ...)
     K_AFFINE = 1,        // a[0..5]: Pillow affine_fixed 16.16 coefficients
-    K_SHIFT = 2,         // a[0]=dx, a[1]=dy : out[y][x] = in[y+dy][x+dx]
+    K_SHIFT = 2,         // a[0]=dx, a[1]=dy, a[2]=bx, a[3]=by : out[y][x] = in[y+dy+(y>=by)][x+dx+(x>=bx)]
+                         //   (bx/by: index from which Pillow's accumulated float offset has rounded
+                         //    up to the next integer - at most one such break per axis)
     K_LUT = 3,           // a[0]=solarize threshold (0..256), a[1]=AND mask : static per-channel LUT
     K_AUTOCONTRAST = 4,  // histogram -> fp64 LUT
     K_EQUALIZE = 5,      // histogram -> integer prefix LUT
@@ -189,7 +191,7 @@ template <int L> struct Level {
             return Level<L - 1>::at(c, xin, yin);
         }
         case K_SHIFT: {      // Pillow ImagingScaleAffine with unit scale: augmentations.py:32,40,47,54
-            int xin = x + o.a[0], yin = y + o.a[1];
+            int xin = x + o.a[0] + (x >= o.a[2]), yin = y + o.a[1] + (y >= o.a[3]);
             if ((unsigned)xin >= (unsigned)c.W || (unsigned)yin >= (unsigned)c.H) return 0u;
             return Level<L - 1>::at(c, xin, yin);
         }

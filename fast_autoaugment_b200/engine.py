@@ -288,3 +288,32 @@ def augment_batch(policy: CompiledPolicy, batch_u8: torch.Tensor, tail: TailSpec
                                         d_p.data_ptr(), float(np.float32(lam)), float(np.float32(1 - lam)),
                                         stream))
     return out
+
+
+class FusedAugmenter:
+    """Pre-bound production launch: fused Philox sampling + augmentation in ONE kernel launch and
+    one ctypes call per batch (no per-call Python allocation), for 2-op policies.
+
+        aug = FusedAugmenter(policy, tail, h, w, seed)
+        aug(batch_u8_cuda, out_cuda, first_index)     # asynchronous on the current stream
+    """
+
+    def __init__(self, policy: CompiledPolicy, tail: TailSpec, h: int, w: int, seed: int = 0):
+        if policy.n_op > _lib.MAX_FUSED_OPS:
+            raise ValueError("FusedAugmenter handles policies of at most 2 ops; use augment_batch")
+        self.policy, self.tail, self.h, self.w = policy, tail, h, w
+        self.t = tail.c_struct(h, w)
+        self.rng = make_rng(seed, 0, tail)
+        self._t_ref, self._rng_ref = C.byref(self.t), C.byref(self.rng)
+        self.out_shape = ((0, self.t.out_h, self.t.out_w, 3) if tail.out_dtype == torch.uint8
+                          else (0, 3, self.t.out_h, self.t.out_w))
+
+    def empty_out(self, batch, device="cuda"):
+        return torch.empty((batch,) + tuple(self.out_shape[1:]), dtype=self.tail.out_dtype, device=device)
+
+    def __call__(self, batch_u8: torch.Tensor, out: torch.Tensor, first_index: int = 0, stream=None):
+        self.rng.first_index = first_index
+        s = stream if stream is not None else torch.cuda.current_stream(batch_u8.device).cuda_stream
+        check(lib.faa_augment(self.policy.handle, batch_u8.data_ptr(), out.data_ptr(), batch_u8.shape[0], self.h,
+                              self.w, self._t_ref, None, None, self._rng_ref, 0, C.c_void_p(s)))
+        return out

@@ -171,3 +171,18 @@ def test_fused_mixup_matches_reference_formula(emu):
     assert lam2 == lam
     got = emu_augment(emu, pol, batch, samples, boxes, tail, norm, partner=perm.numpy(), lam=lam)
     assert np.array_equal(got, want.numpy())
+
+
+def test_translate_accumulator_break(emu):
+    """TranslateX/Y at level 0.75 on 380 px: v*W = 85.50000000000001, Pillow's accumulated
+    offset snaps to the next integer part-way through the row -> two different shifts"""
+    policies = [[("TranslateX", 1.0, 0.75)], [("TranslateY", 1.0, 0.75)], [("TranslateX", 1.0, 0.25)]]
+    pol = CompiledPolicy(policies)
+    recs = [pol.compiled_op(380, 380, s, 0, sg) for s in range(3) for sg in (0, 1)]
+    assert any(r[0] == 2 and (r[3] < 380 or r[4] < 380) for r in recs)       # a break index is present
+    batch = synth_batch(24, (380, 380), seed=1)
+    seed_all(3)
+    want = _policy_oracle(policies, batch)
+    seed_all(3)
+    samples, boxes = pol.sample_parity(len(batch), 380, 380)
+    assert np.array_equal(emu_augment(emu, pol, batch, samples, boxes), want)
