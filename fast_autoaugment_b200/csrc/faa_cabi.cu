@@ -202,6 +202,7 @@ struct faa_policy {
     float norm_mean[3] = {-1e30f, 0, 0}, norm_std[3] = {0, 0, 0};
     float norm_host[768];
     // scratch of faa_augment_host
+    void* d_progs = nullptr; size_t d_progs_bytes = 0;
     void* d_in = nullptr; size_t d_in_bytes = 0;
     void* d_out = nullptr; size_t d_out_bytes = 0;
     void* h_in_stage = nullptr; size_t h_in_bytes = 0;
@@ -279,6 +280,7 @@ int faa_policy_destroy(faa_policy_t* p) {
     for (auto& kv : p->dev_tables) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
     if (p->d_probs) cudaFree(p->d_probs);
     if (p->d_norm) cudaFree(p->d_norm);
+    if (p->d_progs) cudaFree(p->d_progs);
     if (p->d_in) cudaFree(p->d_in);
     if (p->d_out) cudaFree(p->d_out);
     if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
@@ -450,7 +452,7 @@ static uint16_t bits16(int dtype, float v) {
     __nv_bfloat16 b = __float2bfloat16_rn(v); return __bfloat16_as_ushort(b);
 }
 
-static int normalisation(faa_policy* p, const faa_tail_t* tail, AugParams& P, cudaStream_t stream) {
+static int normalisation(faa_policy* p, const faa_tail_t* tail, AugParams& P, bool& use_tab, cudaStream_t stream) {
     bool same = true;
     for (int c = 0; c < 3; ++c) same = same && p->norm_mean[c] == tail->mean[c] && p->norm_std[c] == tail->std[c];
     if (!p->d_norm) { CK(cudaMalloc(&p->d_norm, 768 * sizeof(float))); same = false; }
@@ -479,7 +481,7 @@ static int normalisation(faa_policy* p, const faa_tail_t* tail, AugParams& P, cu
                 if (bits16(tail->out_dtype, f) != bits16(tail->out_dtype, p->norm_host[c * 256 + u])) fma_ok = false;
             }
     }
-    P.use_tab = fma_ok ? 0 : 1;
+    use_tab = !fma_ok;
     return FAA_OK;
 }
 
@@ -501,11 +503,12 @@ int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t
     if (int e = ensure_device()) return e;
     const OpRec* d_ops = nullptr;
     if (int e = device_table(p, h, w, true, &d_ops)) return e;
-    PhiloxParams P;
-    P.ops = d_ops; P.probs = p->d_probs; memcpy(&P.rng, rng, sizeof(RngCfg));
-    P.samples = reinterpret_cast<Sample*>(d_samples); P.boxes = reinterpret_cast<Box*>(d_boxes);
-    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.n_sub = p->n_sub; P.n_op = p->n_op;
-    CK(launch_philox(P, (cudaStream_t)stream));
+    ResolveParams R; memset(&R, 0, sizeof R);
+    R.ops = d_ops; R.probs = p->d_probs; memcpy(&R.rng, rng, sizeof(RngCfg));
+    R.samples_out = reinterpret_cast<Sample*>(d_samples); R.boxes_out = reinterpret_cast<Box*>(d_boxes);
+    R.first = 0; R.n = batch; R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
+    R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = 0; R.apply_tail = 1;
+    CK(launch_resolve(R, (cudaStream_t)stream));
     if (batch > 0) g_launches++;
     return FAA_OK;
 }
@@ -513,7 +516,7 @@ int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t
 static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch,
                           int h, int w, const faa_tail_t* tail, const faa_sample_t* d_samples,
                           const faa_box_t* d_boxes, const faa_rng_t* rng, int op_base, const int32_t* d_partner,
-                          float lam, float oml, int apply_tail, void* stream) {
+                          float lam, float oml, int apply_tail, void* stream_v) {
     if (!p || (!d_in_all && batch > 0) || (!d_out && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
     if (batch < 0 || first < 0 || first + batch > n_all) return fail(FAA_ERR_VALUE, "bad batch range");
     if (int e = check_shape(h, w)) return e;
@@ -522,22 +525,44 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (op_base < 0 || op_base >= p->n_op) return fail(FAA_ERR_VALUE, "op_base out of range");
     if (tail->out_dtype == FAA_U8_HWC && d_partner) return fail(FAA_ERR_UNSUPPORTED, "mixup needs a float output");
     if (int e = ensure_device()) return e;
+    if (batch == 0) return FAA_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
     const OpRec* d_ops = nullptr;
     // resolved samples can only reference ops the host sampler validated; Philox can pick anything
     if (int e = device_table(p, h, w, d_samples == nullptr, &d_ops)) return e;
+    {   // per-image program buffer (grown, never shrunk; stream-ordered reuse)
+        std::lock_guard<std::mutex> lk(p->mu);
+        size_t need = (size_t)n_all * sizeof(Prog);
+        if (p->d_progs_bytes < need) {
+            if (p->d_progs) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(p->d_progs)); p->d_progs = nullptr; p->d_progs_bytes = 0; }
+            need = need < 65536 ? 65536 : need * 2;
+            CK(cudaMalloc(&p->d_progs, need));
+            p->d_progs_bytes = need;
+        }
+    }
+    // launch 1: decisions -> programs (the whole pool when partners may be anywhere in it)
+    ResolveParams R; memset(&R, 0, sizeof R);
+    R.ops = d_ops; R.probs = p->d_probs;
+    R.samples = reinterpret_cast<const Sample*>(d_samples); R.boxes = reinterpret_cast<const Box*>(d_boxes);
+    R.progs = reinterpret_cast<Prog*>(p->d_progs);
+    if (rng) memcpy(&R.rng, rng, sizeof(RngCfg));
+    R.first = d_partner ? 0 : first; R.n = d_partner ? n_all : batch;
+    R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
+    R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = op_base; R.apply_tail = apply_tail;
+    CK(launch_resolve(R, stream));
+    g_launches++;
+    // launch 2: pixels
     AugParams P; memset(&P, 0, sizeof P);
-    P.in = d_in_all; P.out = d_out; P.ops = d_ops; P.probs = p->d_probs;
-    P.samples = reinterpret_cast<const Sample*>(d_samples); P.boxes = reinterpret_cast<const Box*>(d_boxes);
+    P.in = d_in_all; P.out = d_out; P.progs = reinterpret_cast<const Prog*>(p->d_progs);
     P.partner = d_partner;
-    if (rng) memcpy(&P.rng, rng, sizeof(RngCfg));
-    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w;
-    P.n_sub = p->n_sub; P.n_op = p->n_op; P.op_base = op_base; P.first = first;
-    P.apply_tail = apply_tail; P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
+    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.first = first;
+    P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
     P.lam = lam; P.one_minus_lam = oml;
-    if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, (cudaStream_t)stream)) return e; }
+    bool use_tab = false;
+    if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
     P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
-    CK(launch_augment(P, tail->out_dtype, (cudaStream_t)stream));
-    if (batch > 0) g_launches++;
+    CK(launch_augment(P, tail->out_dtype, use_tab, stream));
+    g_launches++;
     return FAA_OK;
 }
 
@@ -630,6 +655,15 @@ int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_
         dst = p->h_out_stage;
     }
 
+    // tables the side streams will read are uploaded on `stream` before the fork
+    if (tail->out_dtype != FAA_U8_HWC) {
+        AugParams dummy; bool tab = false;
+        if (int e = normalisation(p, tail, dummy, tab, stream)) return e;
+    }
+    {
+        const OpRec* d_ops = nullptr;
+        if (int e = device_table(p, h, w, true, &d_ops)) return e;
+    }
     // chunked pipeline on two side streams: H2D(c+1) overlaps kernel(c) and D2H(c)
     int chunks = batch >= 64 ? 8 : (batch >= 8 ? 2 : 1);
     CK(cudaEventRecord(p->ev_fork, stream));

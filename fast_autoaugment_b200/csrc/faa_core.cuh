@@ -14,6 +14,7 @@
 // whole chain needs no second image buffer and no barrier between ops; only the ops that
 // need whole-image statistics (AutoContrast, Equalize, Contrast) cost one extra pass.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -147,7 +148,7 @@ struct Ctx {
 };
 
 FAA_HD uint32_t load_raw(const Ctx& c, int x, int y) {
-    const uint8_t* p = c.raw + ((size_t)y * (size_t)c.W + (size_t)x) * 3u;
+    const uint8_t* p = c.raw + (uint32_t)(y * c.W + x) * 3u;      // H, W <= 8192: fits 32 bits
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
 #else
@@ -178,43 +179,38 @@ template <> struct Level<0> {
     static FAA_HD uint32_t at(const Ctx& c, int x, int y) { return load_raw(c, x, y); }
 };
 
-// value of the image after the first L op slots, at (x, y) of that image
+// value of the image after the first L op slots, at (x, y) of that image.
+// One call site per level for the centre tap (keeps the inlined code small).
 template <int L> struct Level {
     static FAA_HD uint32_t at(const Ctx& c, int x, int y) {
         const OpRec& o = c.op[L - 1];
-        switch (o.kind) {
-        case K_AFFINE: {     // Pillow affine_fixed: augmentations.py:17,24,61 (NEAREST, zero fill)
+        const int k = o.kind;
+        if (k == K_AFFINE) {          // Pillow affine_fixed: augmentations.py:17,24,61 (NEAREST, zero fill)
             int xin = (o.a[2] + o.a[0] * x + o.a[1] * y) >> 16;
-            if ((unsigned)xin >= (unsigned)c.W) return 0u;
             int yin = (o.a[5] + o.a[3] * x + o.a[4] * y) >> 16;
-            if ((unsigned)yin >= (unsigned)c.H) return 0u;
-            return Level<L - 1>::at(c, xin, yin);
-        }
-        case K_SHIFT: {      // Pillow ImagingScaleAffine with unit scale: augmentations.py:32,40,47,54
+            if ((unsigned)xin >= (unsigned)c.W || (unsigned)yin >= (unsigned)c.H) return 0u;
+            x = xin; y = yin;
+        } else if (k == K_SHIFT) {    // Pillow ImagingScaleAffine, unit scale: augmentations.py:32,40,47,54
             int xin = x + o.a[0] + (x >= o.a[2]), yin = y + o.a[1] + (y >= o.a[3]);
             if ((unsigned)xin >= (unsigned)c.W || (unsigned)yin >= (unsigned)c.H) return 0u;
-            return Level<L - 1>::at(c, xin, yin);
+            x = xin; y = yin;
         }
-        case K_SHARPNESS: {  // augmentations.py:112-114: blend(SMOOTH(img), img, v)
-            uint32_t ctr = Level<L - 1>::at(c, x, y);
-            if (x == 0 || y == 0 || x == c.W - 1 || y == c.H - 1) return ctr;   // border copied
-            uint32_t s0 = 4u * (ctr & 255u), s1 = 4u * ((ctr >> 8) & 255u), s2 = 4u * ((ctr >> 16) & 255u);
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    uint32_t q = (dx == 0 && dy == 0) ? ctr : Level<L - 1>::at(c, x + dx, y + dy);
-                    s0 += q & 255u; s1 += (q >> 8) & 255u; s2 += (q >> 16) & 255u;
-                }
-            // [1 1 1;1 5 1;1 1 1]/13 rounded half up == (2S+13)/26
-            s0 = (2u * s0 + 13u) / 26u; s1 = (2u * s1 + 13u) / 26u; s2 = (2u * s2 + 13u) / 26u;
-            float al = bits_to_float(o.a[0]); bool clip = o.a[1] != 0;
-            return blend_u8(s0, ctr & 255u, al, clip) | (blend_u8(s1, (ctr >> 8) & 255u, al, clip) << 8) |
-                   (blend_u8(s2, (ctr >> 16) & 255u, al, clip) << 16);
+        uint32_t p = Level<L - 1>::at(c, x, y);
+        if (k <= K_SHIFT) return p;                                  // NONE / AFFINE / SHIFT
+        if (k != K_SHARPNESS) return apply_pointwise(c, L - 1, p, x, y);
+        // augmentations.py:112-114: blend(SMOOTH(img), img, v); 1-px border copied
+        if (x == 0 || y == 0 || x == c.W - 1 || y == c.H - 1) return p;
+        uint32_t s0 = 4u * (p & 255u), s1 = 4u * ((p >> 8) & 255u), s2 = 4u * ((p >> 16) & 255u);
+        for (int t = 0; t < 9; ++t) {
+            int dx = t % 3 - 1, dy = t / 3 - 1;
+            uint32_t q = (t == 4) ? p : Level<L - 1>::at(c, x + dx, y + dy);
+            s0 += q & 255u; s1 += (q >> 8) & 255u; s2 += (q >> 16) & 255u;
         }
-        case K_NONE:
-            return Level<L - 1>::at(c, x, y);
-        default:
-            return apply_pointwise(c, L - 1, Level<L - 1>::at(c, x, y), x, y);
-        }
+        // [1 1 1;1 5 1;1 1 1]/13 rounded half up == (2S+13)/26
+        s0 = (2u * s0 + 13u) / 26u; s1 = (2u * s1 + 13u) / 26u; s2 = (2u * s2 + 13u) / 26u;
+        float al = bits_to_float(o.a[0]); bool clip = o.a[1] != 0;
+        return blend_u8(s0, p & 255u, al, clip) | (blend_u8(s1, (p >> 8) & 255u, al, clip) << 8) |
+               (blend_u8(s2, (p >> 16) & 255u, al, clip) << 16);
     }
 };
 
@@ -387,5 +383,60 @@ FAA_HD void philox_sample(const RngCfg& r, uint64_t index, const OpRec* ops, con
 // fast exact division of q by d via a 32-bit reciprocal (valid while q*d < 2^32)
 FAA_HD uint32_t recip32(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
 FAA_HD uint32_t fastdiv(uint32_t q, uint32_t rcp) { return umulhi32(q, rcp); }
+
+// ------------------------------------------------------- per-image program --
+// What the resolve step hands to the pixel kernel for one image: the two applied op records,
+// clipped Cutout boxes, the tail decisions and the evaluation class of the final pass.
+enum ProgClass : uint8_t {
+    C_PLAIN = 0,     // no op applied, aligned: 12-byte vector loads straight to the store
+    C_LUT = 1,       // every applied op is a per-channel LUT (static / hist / blend-with-const), aligned
+    C_POINT = 2,     // pointwise incl. Color / Cutout, aligned
+    C_GENERIC = 3    // geometric ops, Sharpness, or unaligned rows: per-pixel lazy evaluation
+};
+
+struct Prog {        // 96 bytes
+    OpRec op[2];
+    Box box[2];
+    int16_t zero_box[4];
+    int8_t crop_dy, crop_dx; uint8_t flip; uint8_t cls;
+    uint8_t stat_mask;           // bit j: slot j needs whole-image statistics
+    uint8_t lut_mask;            // bit j: slot j is evaluated through a 3x256 LUT
+    uint8_t pad[2];
+};
+
+FAA_HD bool kind_is_lutlike(int k) { return k == K_NONE || kind_uses_lut(k); }
+
+// Sample + boxes -> Prog.  ops: compiled table [n_sub][n_op][2]; boxes: this sample's n_op boxes.
+FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, int n_op, int op_base,
+                       int apply_tail, int H, int W, int out_w, Prog& g) {
+    Sample s = s_in;
+    if (!apply_tail) { s.crop_dx = s.crop_dy = 0; s.flip = 0; s.zero_box[0] = s.zero_box[1] = s.zero_box[2] = s.zero_box[3] = 0; }
+    g.crop_dy = s.crop_dy; g.crop_dx = s.crop_dx; g.flip = s.flip;
+    for (int i = 0; i < 4; ++i) g.zero_box[i] = s.zero_box[i];
+    g.stat_mask = 0; g.lut_mask = 0; g.pad[0] = g.pad[1] = 0;
+    bool all_point = true, all_lut = true, any = false;
+    for (int j = 0; j < 2; ++j) {
+        int jj = op_base + j;
+        OpRec o; o.kind = K_NONE; o.a[0] = o.a[1] = o.a[2] = o.a[3] = o.a[4] = o.a[5] = 0; o.draw = 0;
+        if (jj < n_op && ((s.gate >> jj) & 1u)) o = ops[((size_t)s.sub * n_op + jj) * 2 + ((s.sign >> jj) & 1u)];
+        Box b; b.x0 = b.y0 = 0; b.x1 = b.y1 = -1;
+        if (o.kind == K_CUTOUT) {                 // ImageDraw.rectangle clips to the image
+            b = boxes[jj];
+            if (b.x0 < 0) b.x0 = 0;
+            if (b.y0 < 0) b.y0 = 0;
+            if (b.x1 > W - 1) b.x1 = (int16_t)(W - 1);
+            if (b.y1 > H - 1) b.y1 = (int16_t)(H - 1);
+            if (b.x1 < b.x0 || b.y1 < b.y0) o.kind = K_NONE;
+        }
+        g.op[j] = o; g.box[j] = b;
+        if (kind_needs_hist(o.kind) || kind_needs_mean(o.kind)) g.stat_mask |= (uint8_t)(1u << j);
+        if (kind_uses_lut(o.kind)) g.lut_mask |= (uint8_t)(1u << j);
+        all_point = all_point && kind_is_pointwise(o.kind);
+        all_lut = all_lut && kind_is_lutlike(o.kind);
+        any = any || o.kind != K_NONE;
+    }
+    const bool aligned = ((W & 3) == 0) && ((out_w & 3) == 0) && ((s.crop_dx & 3) == 0);
+    g.cls = !aligned || !all_point ? C_GENERIC : !any ? C_PLAIN : all_lut ? C_LUT : C_POINT;
+}
 
 }  // namespace faa

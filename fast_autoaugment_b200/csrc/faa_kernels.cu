@@ -1,23 +1,32 @@
 // faa_kernels.cu - sm_100a kernels of the augmentation hot path.
 //
-// One thread-block CLUSTER per image: the image's rows are split into `bands` row bands,
-// one CTA each (cluster dims = (bands,1,1), grid = (bands, batch)).  Every CTA
-//   1. resolves the image's decisions (sub-policy, gates, signs, boxes, crop/flip/zero-box)
-//      from the per-sample record - or draws them itself (fused Philox mode),
-//   2. for each op that needs whole-image statistics (AutoContrast / Equalize histogram,
-//      Contrast mean luma) scans its band of the *intermediate* image, reduces the partial
-//      statistics across the cluster through distributed shared memory, and builds the
-//      3x256-byte LUT of that op,
-//   3. streams its band of the OUTPUT: tail index map (zero box, flip, crop) -> lazy
-//      evaluation of the op chain back to the raw uint8 pixels -> ToTensor+Normalize ->
-//      NCHW fp16/bf16/fp32 (or uint8 HWC) vector stores.
-// With a Mixup partner the same evaluation runs for the partner image and the two
-// normalised values are mixed in fp32 before the store (aug_mixup.py:21).
+// Two launches per batch:
+//   faa_resolve_kernel   one THREAD per image: per-sample decisions (given records, or drawn
+//                        with Philox4x32-10 keyed by (seed, global sample index)) -> a 96-byte
+//                        per-image program: the two applied op records, clipped Cutout boxes,
+//                        crop / flip / zero-box, and the evaluation CLASS of the image.
+//   faa_augment_kernel   one thread-block CLUSTER per image, one CTA per row band
+//                        (cluster dims (bands,1,1), grid (bands, batch)):
+//     1. ops that need whole-image statistics (AutoContrast / Equalize histogram, Contrast
+//        mean luma): each CTA scans its band of the intermediate image, partial statistics are
+//        reduced across the cluster through distributed shared memory, every CTA builds the
+//        op's 3x256-byte LUT; LUT-only programs are composed into ONE LUT;
+//     2. the CTA streams its band of the OUTPUT with the loop specialised for the image's class:
+//          PLAIN   12-byte vector loads -> normalise -> 8-byte plane stores
+//          LUT     + one composed per-channel LUT lookup
+//          POINT   + pointwise ops in registers (Color, Cutout, LUTs)
+//          GENERIC tail index map (zero box, flip, crop) -> lazy evaluation of the op chain
+//                  back to the raw pixels (16.16 fixed-point gathers, 3x3 Sharpness ...)
+//        followed by ToTensor+Normalize and NCHW fp16/bf16/fp32 (or uint8 HWC) vector stores.
+//   With a Mixup partner the same evaluation runs for the partner image and the normalised
+//   values are mixed in fp32 before the store (aug_mixup.py:21).
 //
 // Algorithmic HBM bytes per image: 3*H*W read + out_elem*3*out_h*out_w written.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "faa_kernels.cuh"
 
@@ -28,14 +37,13 @@ namespace faa {
 constexpr int kThreads = 256;
 
 struct __align__(16) ImgState {
+    Prog prog;                  // 96 B
     uint32_t hist[2][768];      // per-slot local partial histograms (read remotely through DSMEM)
     uint32_t tot[768];          // cluster-reduced histogram of the slot being built
     uint8_t lut[2][768];
+    uint8_t lutc[768];          // composed LUT (C_LUT programs)
     HistPart parts[3][32];
     unsigned long long suml[2]; // per-slot local partial luma sums
-    Sample smp;
-    Box box[2];
-    OpRec op[2];
 };
 
 struct FastDiv {
@@ -45,114 +53,115 @@ struct FastDiv {
 };
 
 // ---------------------------------------------------------------------------------------
-// step 1: decisions -> smem
-__device__ void load_program(const AugParams& P, int idx, ImgState& st) {
-    if (threadIdx.x == 0) {
-        Box bx[8];
-        Sample s;
-        if (P.samples != nullptr) {
-            s = P.samples[idx];
-            for (int j = 0; j < 2; ++j) {
-                int jj = P.op_base + j;
-                if (jj < P.n_op && P.boxes != nullptr) bx[jj] = P.boxes[(size_t)idx * P.n_op + jj];
-                else if (jj < 8) { bx[jj].x0 = bx[jj].y0 = 0; bx[jj].x1 = bx[jj].y1 = -1; }
-            }
-        } else {
-            philox_sample(P.rng, P.rng.first_index + (uint64_t)idx, P.ops, P.probs, P.n_sub, P.n_op,
-                          P.H, P.W, P.out_h, P.out_w, s, bx);
+__global__ void faa_resolve_kernel(const __grid_constant__ ResolveParams P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    const int i = P.first + t;
+    Sample s;
+    Box bx[8];
+    if (P.samples != nullptr) {
+        s = P.samples[i];
+        for (int j = 0; j < P.n_op; ++j) {
+            if (P.boxes != nullptr) bx[j] = P.boxes[(size_t)i * P.n_op + j];
+            else { bx[j].x0 = bx[j].y0 = 0; bx[j].x1 = bx[j].y1 = -1; }
         }
-        if (!P.apply_tail) { s.crop_dx = s.crop_dy = 0; s.flip = 0; }
-        st.smp = s;
-        for (int j = 0; j < 2; ++j) {
-            int jj = P.op_base + j;
-            OpRec o; o.kind = K_NONE; o.a[0] = o.a[1] = o.a[2] = o.a[3] = o.a[4] = o.a[5] = 0; o.draw = 0;
-            if (jj < P.n_op && ((s.gate >> jj) & 1u))
-                o = P.ops[((size_t)s.sub * P.n_op + jj) * 2 + ((s.sign >> jj) & 1u)];
-            st.op[j] = o;
-            Box b; b.x0 = b.y0 = 0; b.x1 = b.y1 = -1;
-            if (o.kind == K_CUTOUT) {        // ImageDraw.rectangle clips to the image
-                b = bx[jj];
-                if (b.x0 < 0) b.x0 = 0;
-                if (b.y0 < 0) b.y0 = 0;
-                if (b.x1 > P.W - 1) b.x1 = (int16_t)(P.W - 1);
-                if (b.y1 > P.H - 1) b.y1 = (int16_t)(P.H - 1);
-            }
-            st.box[j] = b;
-            st.suml[j] = 0ull;
-        }
+    } else {
+        philox_sample(P.rng, P.rng.first_index + (uint64_t)i, P.ops, P.probs, P.n_sub, P.n_op, P.H, P.W,
+                      P.out_h, P.out_w, s, bx);
     }
-    for (int i = threadIdx.x; i < 2 * 768; i += blockDim.x) (&st.hist[0][0])[i] = 0u;
+    if (P.progs != nullptr) {
+        Prog g;
+        build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, g);
+        P.progs[i] = g;
+    }
+    if (P.samples_out != nullptr) P.samples_out[i] = s;
+    if (P.boxes_out != nullptr)
+        for (int j = 0; j < P.n_op; ++j) P.boxes_out[(size_t)i * P.n_op + j] = bx[j];
 }
 
-__device__ __forceinline__ Ctx make_ctx(const AugParams& P, int idx, const ImgState& st) {
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ Ctx make_ctx(const uint8_t* raw, int H, int W, const ImgState& st) {
     Ctx c;
-    c.raw = P.in + (size_t)idx * (size_t)P.H * (size_t)P.W * 3u;
-    c.H = P.H; c.W = P.W;
-    c.op[0] = st.op[0]; c.op[1] = st.op[1];
-    c.box[0] = st.box[0]; c.box[1] = st.box[1];
+    c.raw = raw; c.H = H; c.W = W;
+    c.op[0] = st.prog.op[0]; c.op[1] = st.prog.op[1];
+    c.box[0] = st.prog.box[0]; c.box[1] = st.prog.box[1];
     c.lut[0] = st.lut[0]; c.lut[1] = st.lut[1];
     return c;
 }
 
-// ---------------------------------------------------------------------------------------
-// step 2: statistics of the image in front of slot L (0 or 1) over rows [y0, y1)
+__device__ __forceinline__ void unpack12(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t q[4]) {
+    q[0] = w0 & 0xFFFFFFu;
+    q[1] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8);
+    q[2] = (w1 >> 16) | ((w2 & 0xFFu) << 16);
+    q[3] = w2 >> 8;
+}
+
+// statistics of the image in front of slot L (0 or 1) over rows [y0, y1)
 template <int L>
 __device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_t* hist, unsigned long long* suml) {
-    const uint32_t n = (uint32_t)(y1 - y0) * (uint32_t)c.W;
-    FastDiv dw; dw.init((uint32_t)c.W);
-    if (kind == K_CONTRAST) {
-        uint32_t local = 0;
+    const bool mean = kind == K_CONTRAST;
+    uint32_t local = 0;
+    if (L == 0 && (c.W & 3) == 0) {
+        // raw image: 4 pixels per thread from three aligned 32-bit loads
+        const uint32_t nq = (uint32_t)(y1 - y0) * (uint32_t)c.W / 4u;
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(c.raw + (uint32_t)y0 * (uint32_t)c.W * 3u);
+        for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
+            uint32_t q[4];
+            unpack12(__ldg(base + 3u * i), __ldg(base + 3u * i + 1), __ldg(base + 3u * i + 2), q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (mean) local += luma_of(q[k]);
+                else {
+                    atomicAdd(&hist[q[k] & 255u], 1u);
+                    atomicAdd(&hist[256u + ((q[k] >> 8) & 255u)], 1u);
+                    atomicAdd(&hist[512u + (q[k] >> 16)], 1u);
+                }
+            }
+        }
+    } else {
+        const uint32_t n = (uint32_t)(y1 - y0) * (uint32_t)c.W;
+        FastDiv dw; dw.init((uint32_t)c.W);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             uint32_t r = dw.div(i);
-            local += luma_of(Level<L>::at(c, (int)(i - r * c.W), y0 + (int)r));
+            uint32_t p = Level<L>::at(c, (int)(i - r * c.W), y0 + (int)r);
+            if (mean) local += luma_of(p);
+            else {
+                atomicAdd(&hist[p & 255u], 1u);
+                atomicAdd(&hist[256u + ((p >> 8) & 255u)], 1u);
+                atomicAdd(&hist[512u + (p >> 16)], 1u);
+            }
         }
+    }
+    if (mean) {
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if ((threadIdx.x & 31) == 0) atomicAdd(suml, (unsigned long long)local);
-    } else {
-        const int lane = threadIdx.x & 31;
-        for (uint32_t base = 0; base < n; base += blockDim.x) {      // warp-uniform trip count
-            const uint32_t i = base + threadIdx.x;
-            const bool valid = i < n;
-            const uint32_t act = __ballot_sync(0xffffffffu, valid);
-            if (!valid) continue;
-            uint32_t r = dw.div(i);
-            uint32_t p = Level<L>::at(c, (int)(i - r * c.W), y0 + (int)r);
-            // warp-aggregated increments: lanes that hit the same bin elect one adder
-            // (constant-colour regions would otherwise serialise 32-way on one bank)
-            uint32_t b0 = p & 255u, b1 = 256u + ((p >> 8) & 255u), b2 = 512u + (p >> 16);
-            uint32_t m0 = __match_any_sync(act, b0);
-            if (lane == __ffs(m0) - 1) atomicAdd(&hist[b0], (uint32_t)__popc(m0));
-            uint32_t m1 = __match_any_sync(act, b1);
-            if (lane == __ffs(m1) - 1) atomicAdd(&hist[b1], (uint32_t)__popc(m1));
-            uint32_t m2 = __match_any_sync(act, b2);
-            if (lane == __ffs(m2) - 1) atomicAdd(&hist[b2], (uint32_t)__popc(m2));
-        }
     }
 }
 
 // reduce slot j's partial statistics over the cluster and build its LUT
-__device__ void build_slot_lut(const AugParams& P, ImgState& st, int j, cg::cluster_group& cluster) {
-    const int kind = st.op[j].kind;
+__device__ void build_slot_lut(int bands, uint32_t n_pixels, ImgState& st, int j, cg::cluster_group& cluster) {
+    const OpRec o = st.prog.op[j];
+    const int kind = o.kind;
     const bool stats = kind_needs_hist(kind) || kind_needs_mean(kind);
     uint32_t mean = 0;
     if (stats) {
-        if (P.bands > 1) cluster.sync(); else __syncthreads();     // partials complete everywhere
+        if (bands > 1) cluster.sync(); else __syncthreads();     // partials complete everywhere
         if (kind_needs_hist(kind)) {
             for (int i = threadIdx.x; i < 768; i += blockDim.x) {
                 uint32_t t = 0;
-                for (int r = 0; r < P.bands; ++r) {
-                    const uint32_t* rem = (P.bands > 1) ? cluster.map_shared_rank(&st.hist[j][0], r) : &st.hist[j][0];
+                for (int r = 0; r < bands; ++r) {
+                    const uint32_t* rem = (bands > 1) ? cluster.map_shared_rank(&st.hist[j][0], r) : &st.hist[j][0];
                     t += rem[i];
                 }
                 st.tot[i] = t;
             }
         } else {
             unsigned long long t = 0;
-            for (int r = 0; r < P.bands; ++r) {
-                const unsigned long long* rem = (P.bands > 1) ? cluster.map_shared_rank(&st.suml[j], r) : &st.suml[j];
+            for (int r = 0; r < bands; ++r) {
+                const unsigned long long* rem = (bands > 1) ? cluster.map_shared_rank(&st.suml[j], r) : &st.suml[j];
                 t += *rem;
             }
-            mean = contrast_mean(t, (uint32_t)P.H * (uint32_t)P.W);
+            mean = contrast_mean(t, n_pixels);
         }
         __syncthreads();
     }
@@ -161,72 +170,112 @@ __device__ void build_slot_lut(const AugParams& P, ImgState& st, int j, cg::clus
         if (t < 96) st.parts[t >> 5][t & 31] = hist_part(&st.tot[(t >> 5) * 256], t & 31);
         __syncthreads();
         if (t < 96)
-            hist_lut_lane(kind, &st.tot[(t >> 5) * 256], st.parts[t >> 5], t & 31,
-                          (uint32_t)P.H * (uint32_t)P.W, &st.lut[j][(t >> 5) * 256]);
-    } else if (kind_uses_lut(kind)) {
+            hist_lut_lane(kind, &st.tot[(t >> 5) * 256], st.parts[t >> 5], t & 31, n_pixels, &st.lut[j][(t >> 5) * 256]);
+    } else {
         for (int i = threadIdx.x; i < 768; i += blockDim.x)
-            st.lut[j][i] = (uint8_t)lut_entry_static(st.op[j], (uint32_t)(i & 255), mean);
+            st.lut[j][i] = (uint8_t)lut_entry_static(o, (uint32_t)(i & 255), mean);
     }
     __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------
-// step 3 helpers
-__device__ __forceinline__ float normalise(const AugParams& P, int ch, uint32_t u) {
-    return P.use_tab ? __ldg(P.norm_tab + ch * 256 + u) : fmaf((float)u, P.scale[ch], P.bias[ch]);
+// everything before the final pass for one source image
+__device__ bool prepare_image(const AugParams& P, const uint8_t* raw, int band, ImgState& st, cg::cluster_group& cluster) {
+    const uint32_t stat_mask = st.prog.stat_mask, lut_mask = st.prog.lut_mask;
+    if (lut_mask == 0) return false;
+    const int y0 = (int)(((long long)band * P.H) / P.bands);
+    const int y1 = (int)(((long long)(band + 1) * P.H) / P.bands);
+    if (stat_mask) {
+        for (int i = threadIdx.x; i < 2 * 768; i += blockDim.x) (&st.hist[0][0])[i] = 0u;
+        if (threadIdx.x < 2) st.suml[threadIdx.x] = 0ull;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (!((lut_mask >> j) & 1u)) continue;
+        if ((stat_mask >> j) & 1u) {
+            Ctx c = make_ctx(raw, P.H, P.W, st);
+            const int kind = st.prog.op[j].kind;
+            if (j == 0) accumulate_stats<0>(c, kind, y0, y1, st.hist[0], &st.suml[0]);
+            else        accumulate_stats<1>(c, kind, y0, y1, st.hist[1], &st.suml[1]);
+        }
+        build_slot_lut(P.bands, (uint32_t)P.H * (uint32_t)P.W, st, j, cluster);
+    }
+    if (st.prog.cls == C_LUT) {           // one lookup per channel in the final pass
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            uint32_t v = (uint32_t)(i & 255), base = (uint32_t)(i & ~255);
+            if (lut_mask & 1u) v = st.lut[0][base + v];
+            if (lut_mask & 2u) v = st.lut[1][base + v];
+            st.lutc[i] = (uint8_t)v;
+        }
+        __syncthreads();
+    }
+    return stat_mask != 0;
 }
 
-// four consecutive output pixels of row oy starting at ox0, as packed RGB; zmask bit k set
-// when pixel k lies in the CutoutDefault zero box
-__device__ __forceinline__ void quad_pixels(const AugParams& P, const Ctx& c, const Sample& s, bool fast,
-                                            int ox0, int oy, uint32_t px[4], uint32_t& zmask) {
-    zmask = 0;
-    if (fast) {
-        // pointwise-only program, 4-aligned source quad: three 32-bit loads of 12 contiguous bytes
-        const int sx0 = (s.flip ? (P.out_w - 4 - ox0) : ox0) + s.crop_dx;
-        const int ay = oy + s.crop_dy;
-        uint32_t q[4] = {0u, 0u, 0u, 0u};
-        const bool inside = (unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H;
-        if (inside) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(c.raw + ((size_t)ay * c.W + sx0) * 3u);
-            uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-            q[0] = w0 & 0xFFFFFFu;
-            q[1] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8);
-            q[2] = (w1 >> 16) | ((w2 & 0xFFu) << 16);
-            q[3] = w2 >> 8;
+// ---------------------------------------------------------------------------------------
+// final pass building blocks
+struct TailInfo {
+    int crop_dy, crop_dx, flip;
+    int zb0, zb1, zb2, zb3;      // zero box rows [zb0,zb1) x cols [zb2,zb3); empty when off
+};
+
+__device__ __forceinline__ TailInfo make_tail(const AugParams& P, const Prog& g) {
+    TailInfo t;
+    t.crop_dy = g.crop_dy; t.crop_dx = g.crop_dx; t.flip = g.flip;
+    const bool on = P.use_zero_box != 0;
+    t.zb0 = on ? g.zero_box[0] : 0; t.zb1 = on ? g.zero_box[1] : 0;
+    t.zb2 = on ? g.zero_box[2] : 0; t.zb3 = on ? g.zero_box[3] : 0;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t zero_mask(const TailInfo& t, int ox0, int oy) {
+    if (oy < t.zb0 || oy >= t.zb1) return 0u;
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m |= (uint32_t)(ox0 + k >= t.zb2 && ox0 + k < t.zb3) << k;
+    return m;
+}
+
+// aligned classes: the four source pixels of an output quad are 12 contiguous bytes
+template <int CLS>
+__device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, const TailInfo& t, int out_w, int ox0,
+                                         int oy, uint32_t px[4]) {
+    const int sx0 = (t.flip ? (out_w - 4 - ox0) : ox0) + t.crop_dx;
+    const int ay = oy + t.crop_dy;
+    uint32_t q[4] = {0u, 0u, 0u, 0u};
+    if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(c.raw + (uint32_t)(ay * c.W + sx0) * 3u);
+        unpack12(__ldg(w), __ldg(w + 1), __ldg(w + 2), q);
+        if (CLS == C_LUT) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = apply_lut(lutc, q[k]);
+        } else if (CLS == C_POINT) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            px[k] = s.flip ? q[3 - k] : q[k];
-            const int ox = ox0 + k;
-            if (P.use_zero_box && oy >= s.zero_box[0] && oy < s.zero_box[1] && ox >= s.zero_box[2] && ox < s.zero_box[3])
-                zmask |= 1u << k;
-        }
-        return;
     }
+    if (t.flip) { px[0] = q[3]; px[1] = q[2]; px[2] = q[1]; px[3] = q[0]; }
+    else { px[0] = q[0]; px[1] = q[1]; px[2] = q[2]; px[3] = q[3]; }
+}
+
+__device__ __forceinline__ void quad_generic(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
+    const int ay = oy + t.crop_dy;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int ox = ox0 + k;
         px[k] = 0u;
-        if (ox >= P.out_w) continue;
-        int ax, ay; bool inside;
-        if (!tail_source(s, P.use_zero_box != 0, P.out_w, c.H, c.W, ox, oy, ax, ay, inside)) { zmask |= 1u << k; continue; }
-        if (inside) px[k] = Level<2>::at(c, ax, ay);
+        const int ax = (t.flip ? (out_w - 1 - ox) : ox) + t.crop_dx;
+        if (ox < out_w && (unsigned)ax < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) px[k] = Level<2>::at(c, ax, ay);
     }
 }
 
-template <int OUT> struct OutElem;
+template <int OUT> struct OutElem { using T = float; };
 template <> struct OutElem<OUT_F16> { using T = __half; };
 template <> struct OutElem<OUT_BF16> { using T = __nv_bfloat16; };
-template <> struct OutElem<OUT_F32> { using T = float; };
 
 template <int OUT>
-__device__ __forceinline__ void store_plane4(void* out, size_t elem_off, const float v[4], bool vec, int nvalid) {
-    using T = typename OutElem<OUT>::T;
-    T* o = reinterpret_cast<T*>(out) + elem_off;
+__device__ __forceinline__ void store_plane4(typename OutElem<OUT>::T* o, const float v[4], bool vec, int nvalid) {
     if (vec) {
         if constexpr (OUT == OUT_F32) {
             *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -248,11 +297,122 @@ __device__ __forceinline__ void store_plane4(void* out, size_t elem_off, const f
     }
 }
 
+template <bool TAB>
+__device__ __forceinline__ float normalise(const AugParams& P, const float* s_norm, int ch, uint32_t u) {
+    if (TAB) return s_norm[ch * 256 + u];
+    return fmaf((float)u, P.scale[ch], P.bias[ch]);
+}
+
+// normalise + store one quad (single source)
+template <int OUT, bool TAB>
+__device__ __forceinline__ void emit_quad(const AugParams& P, const float* s_norm, void* out_img, int ox0, int oy,
+                                          const uint32_t px_in[4], uint32_t zmask, bool vec) {
+    const int nvalid = min(4, P.out_w - ox0);
+    if constexpr (OUT == OUT_U8_HWC) {
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) px[k] = ((zmask >> k) & 1u) ? 0u : px_in[k];
+        uint8_t* o = reinterpret_cast<uint8_t*>(out_img) + (uint32_t)(oy * P.out_w + ox0) * 3u;
+        if (vec) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(o);
+            w[0] = px[0] | (px[1] << 24);
+            w[1] = (px[1] >> 8) | (px[2] << 16);
+            w[2] = (px[2] >> 16) | (px[3] << 8);
+        } else {
+            for (int k = 0; k < nvalid; ++k) {
+                o[3 * k] = (uint8_t)px[k]; o[3 * k + 1] = (uint8_t)(px[k] >> 8); o[3 * k + 2] = (uint8_t)(px[k] >> 16);
+            }
+        }
+    } else {
+        using T = typename OutElem<OUT>::T;
+        const uint32_t plane = (uint32_t)P.out_h * (uint32_t)P.out_w;
+        T* o = reinterpret_cast<T*>(out_img) + (uint32_t)(oy * P.out_w + ox0);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a = normalise<TAB>(P, s_norm, ch, (px_in[k] >> (8 * ch)) & 255u);
+                v[k] = ((zmask >> k) & 1u) ? 0.0f : a;
+            }
+            store_plane4<OUT>(o + ch * plane, v, vec, nvalid);
+        }
+    }
+}
+
+template <int OUT, bool TAB, int CLS>
+__device__ __forceinline__ void final_pass(const AugParams& P, const float* s_norm, const ImgState& st,
+                                           const uint8_t* raw, void* out_img, int band) {
+    const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
+    const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
+    const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
+    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
+    FastDiv dq; dq.init(qpr);
+    const bool vec = (P.out_w & 3) == 0;
+    const TailInfo t = make_tail(P, st.prog);
+    Ctx c;
+    if (CLS == C_POINT || CLS == C_GENERIC) c = make_ctx(raw, P.H, P.W, st);
+    else { c.raw = raw; c.H = P.H; c.W = P.W; }
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const uint32_t r = dq.div(q);
+        const int ox0 = (int)(q - r * qpr) * 4;
+        const int oy = oy0 + (int)r;
+        uint32_t px[4];
+        if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
+        else quad_vec<CLS>(c, st.lutc, t, P.out_w, ox0, oy, px);
+        emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
+    }
+}
+
+// two sources mixed in fp32 (fused Mixup): class dispatch per quad, both contexts live
+template <int OUT, bool TAB>
+__device__ void final_pass_mix(const AugParams& P, const float* s_norm, const ImgState* st, const uint8_t* raw0,
+                               const uint8_t* raw1, void* out_img, int band) {
+    using T = typename OutElem<OUT>::T;
+    const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
+    const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
+    const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
+    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
+    FastDiv dq; dq.init(qpr);
+    const bool vec = (P.out_w & 3) == 0;
+    const TailInfo t0 = make_tail(P, st[0].prog), t1 = make_tail(P, st[1].prog);
+    const Ctx c0 = make_ctx(raw0, P.H, P.W, st[0]), c1 = make_ctx(raw1, P.H, P.W, st[1]);
+    const int cls0 = st[0].prog.cls, cls1 = st[1].prog.cls;
+    const uint32_t plane = (uint32_t)P.out_h * (uint32_t)P.out_w;
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const uint32_t r = dq.div(q);
+        const int ox0 = (int)(q - r * qpr) * 4;
+        const int oy = oy0 + (int)r;
+        uint32_t pa[4], pb[4];
+        if (cls0 == C_GENERIC) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
+        else if (cls0 == C_LUT) quad_vec<C_LUT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
+        else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
+        if (cls1 == C_GENERIC) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
+        else if (cls1 == C_LUT) quad_vec<C_LUT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
+        else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
+        const uint32_t za = zero_mask(t0, ox0, oy), zb = zero_mask(t1, ox0, oy);
+        const int nvalid = min(4, P.out_w - ox0);
+        T* o = reinterpret_cast<T*>(out_img) + (uint32_t)(oy * P.out_w + ox0);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a = ((za >> k) & 1u) ? 0.0f : normalise<TAB>(P, s_norm, ch, (pa[k] >> (8 * ch)) & 255u);
+                float b = ((zb >> k) & 1u) ? 0.0f : normalise<TAB>(P, s_norm, ch, (pb[k] >> (8 * ch)) & 255u);
+                v[k] = f_add(f_mul(a, P.lam), f_mul(b, P.one_minus_lam));          // aug_mixup.py:21
+            }
+            store_plane4<OUT>(o + ch * plane, v, vec, nvalid);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
-template <int OUT, int NSRC>
-__global__ void __launch_bounds__(kThreads) faa_augment_kernel(const __grid_constant__ AugParams P) {
+template <int OUT, int NSRC, bool TAB>
+__global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st[NSRC];
+    __shared__ float s_norm[TAB ? 768 : 1];
 
     const int band = blockIdx.x;
     const int img = blockIdx.y;
@@ -260,106 +420,41 @@ __global__ void __launch_bounds__(kThreads) faa_augment_kernel(const __grid_cons
     src_idx[0] = P.first + img;
     if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
 
-    // ---- 1. decisions
+    // per-image programs -> shared memory (24 words each)
 #pragma unroll
-    for (int s = 0; s < NSRC; ++s) load_program(P, src_idx[s], st[s]);
+    for (int s = 0; s < NSRC; ++s)
+        if (threadIdx.x < sizeof(Prog) / 4)
+            reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
+                __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
+    if (TAB)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     __syncthreads();
 
-    // ---- 2. statistics + LUTs, slot by slot (cluster-uniform control flow)
-    const int y0 = (int)(((long long)band * P.H) / P.bands);
-    const int y1 = (int)(((long long)(band + 1) * P.H) / P.bands);
-    bool any_stats = false;
-#pragma unroll
-    for (int s = 0; s < NSRC; ++s) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int kind = st[s].op[j].kind;
-            if (kind_needs_hist(kind) || kind_needs_mean(kind)) {
-                any_stats = true;
-                Ctx c = make_ctx(P, src_idx[s], st[s]);
-                if (j == 0) accumulate_stats<0>(c, kind, y0, y1, st[s].hist[0], &st[s].suml[0]);
-                else        accumulate_stats<1>(c, kind, y0, y1, st[s].hist[1], &st[s].suml[1]);
-            }
-            if (kind_uses_lut(kind)) build_slot_lut(P, st[s], j, cluster);
-        }
-    }
-
-    // ---- 3. output band
-    const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
-    const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
-    const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
-    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
-    FastDiv dq; dq.init(qpr);
-    const bool vec = (P.out_w & 3) == 0;
-
-    Ctx c0 = make_ctx(P, src_idx[0], st[0]);
-    const Sample s0 = st[0].smp;
-    const bool geom_ok = ((P.W & 3) == 0) && vec;
-    const bool fast0 = geom_ok && kind_is_pointwise(c0.op[0].kind) && kind_is_pointwise(c0.op[1].kind) &&
-                       ((s0.crop_dx & 3) == 0);
-    Ctx c1; Sample s1; bool fast1 = false;
+    const size_t img_bytes = (size_t)P.H * (size_t)P.W * 3u;
+    const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
+    bool any_stats = prepare_image(P, raw0, band, st[0], cluster);
+    const uint8_t* raw1 = raw0;
     if constexpr (NSRC == 2) {
-        c1 = make_ctx(P, src_idx[1], st[1]);
-        s1 = st[1].smp;
-        fast1 = geom_ok && kind_is_pointwise(c1.op[0].kind) && kind_is_pointwise(c1.op[1].kind) && ((s1.crop_dx & 3) == 0);
+        raw1 = P.in + (size_t)src_idx[1] * img_bytes;
+        any_stats |= prepare_image(P, raw1, band, st[1], cluster);
     }
 
-    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
-        const uint32_t r = dq.div(q);
-        const int ox0 = (int)(q - r * qpr) * 4;
-        const int oy = oy0 + (int)r;
-        const int nvalid = min(4, P.out_w - ox0);
-        uint32_t px[4], zmask;
-        quad_pixels(P, c0, s0, fast0, ox0, oy, px, zmask);
+    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
+    void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
 
-        if constexpr (OUT == OUT_U8_HWC) {
-            uint8_t* o = reinterpret_cast<uint8_t*>(P.out) + (((size_t)img * P.out_h + oy) * P.out_w + ox0) * 3u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if ((zmask >> k) & 1u) px[k] = 0u;
-            if (vec) {
-                uint32_t* w = reinterpret_cast<uint32_t*>(o);
-                w[0] = px[0] | (px[1] << 24);
-                w[1] = (px[1] >> 8) | (px[2] << 16);
-                w[2] = (px[2] >> 16) | (px[3] << 8);
-            } else {
-                for (int k = 0; k < nvalid; ++k) {
-                    o[3 * k] = (uint8_t)px[k]; o[3 * k + 1] = (uint8_t)(px[k] >> 8); o[3 * k + 2] = (uint8_t)(px[k] >> 16);
-                }
-            }
-        } else {
-            uint32_t px1[4], zmask1 = 0;
-            if constexpr (NSRC == 2) quad_pixels(P, c1, s1, fast1, ox0, oy, px1, zmask1);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                float v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float a = ((zmask >> k) & 1u) ? 0.0f : normalise(P, ch, (px[k] >> (8 * ch)) & 255u);
-                    if constexpr (NSRC == 2) {
-                        float b = ((zmask1 >> k) & 1u) ? 0.0f : normalise(P, ch, (px1[k] >> (8 * ch)) & 255u);
-                        a = f_add(f_mul(a, P.lam), f_mul(b, P.one_minus_lam));       // aug_mixup.py:21
-                    }
-                    v[k] = a;
-                }
-                const size_t off = (((size_t)img * 3 + ch) * P.out_h + oy) * (size_t)P.out_w + ox0;
-                store_plane4<OUT>(P.out, off, v, vec, nvalid);
-            }
+    if constexpr (NSRC == 1) {
+        switch (st[0].prog.cls) {
+        case C_PLAIN: final_pass<OUT, TAB, C_PLAIN>(P, s_norm, st[0], raw0, out_img, band); break;
+        case C_LUT:   final_pass<OUT, TAB, C_LUT>(P, s_norm, st[0], raw0, out_img, band); break;
+        case C_POINT: final_pass<OUT, TAB, C_POINT>(P, s_norm, st[0], raw0, out_img, band); break;
+        default:      final_pass<OUT, TAB, C_GENERIC>(P, s_norm, st[0], raw0, out_img, band); break;
         }
+    } else {
+        final_pass_mix<OUT, TAB>(P, s_norm, st, raw0, raw1, out_img, band);
     }
 
     // a CTA must not exit while cluster peers may still read its partial statistics
     if (any_stats && P.bands > 1) cluster.sync();
-}
-
-// ---------------------------------------------------------------------------------------
-__global__ void faa_philox_kernel(const __grid_constant__ PhiloxParams P) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.B) return;
-    Sample s; Box bx[8];
-    philox_sample(P.rng, P.rng.first_index + (uint64_t)i, P.ops, P.probs, P.n_sub, P.n_op, P.H, P.W,
-                  P.out_h, P.out_w, s, bx);
-    P.samples[i] = s;
-    for (int j = 0; j < P.n_op; ++j) P.boxes[(size_t)i * P.n_op + j] = bx[j];
 }
 
 // out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math (aug_mixup.py:13-23)
@@ -382,10 +477,12 @@ int pick_bands(int H, int W, int out_h, int out_w) {
     long long quads = (long long)out_h * ((out_w + 3) / 4);
     int b = 1;
     while (b < 8 && quads / (b * 2) >= 1024 && b * 2 <= H && b * 2 <= out_h) b *= 2;
+    const char* e = getenv("FAA_BANDS");          // tuning knob for experiments
+    if (e && *e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) b = (v <= H && v <= out_h) ? v : b; }
     return b;
 }
 
-template <int OUT, int NSRC>
+template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
@@ -399,24 +496,30 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC>, p);
+    return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
 
-cudaError_t launch_augment(const AugParams& p, int out_type, cudaStream_t stream) {
+template <int OUT>
+static cudaError_t launch_out(const AugParams& p, bool mix, bool tab, cudaStream_t stream) {
+    if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
+    return tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
+}
+
+cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaStream_t stream) {
     if (p.B <= 0) return cudaSuccess;
     const bool mix = p.partner != nullptr;
     switch (out_type) {
-    case OUT_F16:  return mix ? launch_one<OUT_F16, 2>(p, stream)  : launch_one<OUT_F16, 1>(p, stream);
-    case OUT_BF16: return mix ? launch_one<OUT_BF16, 2>(p, stream) : launch_one<OUT_BF16, 1>(p, stream);
-    case OUT_F32:  return mix ? launch_one<OUT_F32, 2>(p, stream)  : launch_one<OUT_F32, 1>(p, stream);
-    case OUT_U8_HWC: return launch_one<OUT_U8_HWC, 1>(p, stream);
+    case OUT_F16:  return launch_out<OUT_F16>(p, mix, use_tab, stream);
+    case OUT_BF16: return launch_out<OUT_BF16>(p, mix, use_tab, stream);
+    case OUT_F32:  return mix ? launch_one<OUT_F32, 2, true>(p, stream) : launch_one<OUT_F32, 1, true>(p, stream);
+    case OUT_U8_HWC: return launch_one<OUT_U8_HWC, 1, false>(p, stream);
     default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_philox(const PhiloxParams& p, cudaStream_t stream) {
-    if (p.B <= 0) return cudaSuccess;
-    faa_philox_kernel<<<(p.B + 127) / 128, 128, 0, stream>>>(p);
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return cudaSuccess;
+    faa_resolve_kernel<<<(p.n + 127) / 128, 128, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -8,35 +8,36 @@ namespace faa {
 
 enum OutType : int32_t { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2, OUT_U8_HWC = 3 };
 
+// step 1 (one thread per image): decisions -> per-image program
+struct ResolveParams {
+    const OpRec* ops;           // compiled policy [n_sub][n_op][2]
+    const double* probs;        // [n_sub][n_op]
+    const Sample* samples;      // [n] resolved decisions, or nullptr -> draw with Philox
+    const Box* boxes;           // [n][n_op] (may be nullptr when no Cutout box is needed)
+    Prog* progs;                // [n] out
+    Sample* samples_out;        // optional [n]
+    Box* boxes_out;             // optional [n][n_op]
+    RngCfg rng;
+    int32_t first, n;           // images [first, first+n) of the arrays above
+    int32_t H, W, out_h, out_w, n_sub, n_op, op_base, apply_tail;
+};
+cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
+
+// step 2 (one cluster per image): pixels
 struct AugParams {
     const uint8_t* in;          // [n_all][H][W][3] uint8
     void* out;                  // [B][3][out_h][out_w] OutT  (or [B][out_h][out_w][3] uint8)
-    const OpRec* ops;           // compiled policy [n_sub][n_op][2]
-    const double* probs;        // [n_sub][n_op]
-    const Sample* samples;      // [n_all] resolved decisions, or nullptr -> fused Philox
-    const Box* boxes;           // [n_all][n_op]
+    const Prog* progs;          // [n_all]
     const int32_t* partner;     // [B] index into [0, n_all) or nullptr (no mixup)
     const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values
-    RngCfg rng;
     int32_t B, H, W, out_h, out_w;
-    int32_t n_sub, n_op, op_base;
     int32_t first;              // index of this launch's image 0 inside the n_all arrays
-    int32_t apply_tail;         // 0 for the intermediate launches of a chained (n_op > 2) policy
     int32_t use_zero_box;
-    int32_t use_tab;            // 1: normalise through norm_tab (exact fp32), 0: fma(scale, bias)
     int32_t bands;              // CTAs (== cluster size) per image
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };
-
-cudaError_t launch_augment(const AugParams& p, int out_type, cudaStream_t stream);
-
-struct PhiloxParams {
-    const OpRec* ops; const double* probs; RngCfg rng;
-    Sample* samples; Box* boxes;
-    int32_t B, H, W, out_h, out_w, n_sub, n_op;
-};
-cudaError_t launch_philox(const PhiloxParams& p, cudaStream_t stream);
+cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaStream_t stream);
 
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,
                          int dtype, float lam, float one_minus_lam, cudaStream_t stream);

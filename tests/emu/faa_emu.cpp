@@ -2,11 +2,12 @@
 //
 // There is no GPU in the build container, so the CPU test-suite cannot run the kernels.
 // This file compiles the very same per-pixel arithmetic header the kernels use
-// (fast_autoaugment_b200/csrc/faa_core.cuh: lazy op-chain evaluation, LUT builders, blend,
-// tail index map, Philox sampler) with g++ and drives it with the kernel's control flow
-// for ONE band per image (cluster size 1), so the arithmetic the GPU will execute is
-// checked against the oracle on the CPU first.  It is not part of the product: the
-// package never loads it, and the product has no CPU fallback.
+// (fast_autoaugment_b200/csrc/faa_core.cuh: program builder and classes, lazy op-chain
+// evaluation, LUT builders, blend, Philox sampler) with g++ and drives it with the kernels'
+// control flow (resolve -> statistics -> LUTs -> class-specialised final pass) for ONE band
+// per image (cluster size 1), so the arithmetic the GPU will execute is checked against the
+// oracle on the CPU first.  It is not part of the product: the package never loads it, and
+// the product has no CPU fallback.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -18,43 +19,18 @@ using namespace faa;
 namespace {
 
 struct State {
+    Prog prog;
     uint32_t hist[2][768];
     uint32_t tot[768];
     uint8_t lut[2][768];
+    uint8_t lutc[768];
     HistPart parts[3][32];
     unsigned long long suml[2];
-    Sample smp;
-    Box box[2];
-    OpRec op[2];
 };
-
-void load_program(const OpRec* ops, int n_op, int op_base, int apply_tail, int H, int W, const Sample& in_s,
-                  const Box* in_boxes, State& st) {
-    Sample s = in_s;
-    if (!apply_tail) { s.crop_dx = s.crop_dy = 0; s.flip = 0; }
-    st.smp = s;
-    for (int j = 0; j < 2; ++j) {
-        int jj = op_base + j;
-        OpRec o; memset(&o, 0, sizeof o); o.kind = K_NONE;
-        if (jj < n_op && ((s.gate >> jj) & 1u)) o = ops[((size_t)s.sub * n_op + jj) * 2 + ((s.sign >> jj) & 1u)];
-        st.op[j] = o;
-        Box b; b.x0 = b.y0 = 0; b.x1 = b.y1 = -1;
-        if (o.kind == K_CUTOUT) {
-            b = in_boxes[jj];
-            if (b.x0 < 0) b.x0 = 0;
-            if (b.y0 < 0) b.y0 = 0;
-            if (b.x1 > W - 1) b.x1 = (int16_t)(W - 1);
-            if (b.y1 > H - 1) b.y1 = (int16_t)(H - 1);
-        }
-        st.box[j] = b;
-        st.suml[j] = 0;
-    }
-    memset(st.hist, 0, sizeof st.hist);
-}
 
 Ctx make_ctx(const uint8_t* raw, int H, int W, const State& st) {
     Ctx c; c.raw = raw; c.H = H; c.W = W;
-    c.op[0] = st.op[0]; c.op[1] = st.op[1]; c.box[0] = st.box[0]; c.box[1] = st.box[1];
+    c.op[0] = st.prog.op[0]; c.op[1] = st.prog.op[1]; c.box[0] = st.prog.box[0]; c.box[1] = st.prog.box[1];
     c.lut[0] = st.lut[0]; c.lut[1] = st.lut[1];
     return c;
 }
@@ -70,7 +46,8 @@ void accumulate(const Ctx& c, int kind, uint32_t* hist, unsigned long long* suml
 }
 
 void build_lut(State& st, int j, int H, int W) {
-    const int kind = st.op[j].kind;
+    const OpRec o = st.prog.op[j];
+    const int kind = o.kind;
     uint32_t mean = 0;
     if (kind_needs_hist(kind)) memcpy(st.tot, st.hist[j], sizeof st.tot);
     if (kind_needs_mean(kind)) mean = contrast_mean(st.suml[j], (uint32_t)H * (uint32_t)W);
@@ -79,58 +56,77 @@ void build_lut(State& st, int j, int H, int W) {
         for (int t = 0; t < 96; ++t)
             hist_lut_lane(kind, &st.tot[(t >> 5) * 256], st.parts[t >> 5], t & 31, (uint32_t)H * (uint32_t)W,
                           &st.lut[j][(t >> 5) * 256]);
-    } else if (kind_uses_lut(kind)) {
-        for (int i = 0; i < 768; ++i) st.lut[j][i] = (uint8_t)lut_entry_static(st.op[j], (uint32_t)(i & 255), mean);
+    } else {
+        for (int i = 0; i < 768; ++i) st.lut[j][i] = (uint8_t)lut_entry_static(o, (uint32_t)(i & 255), mean);
     }
 }
 
 void prepare(const uint8_t* raw, int H, int W, State& st) {
+    const uint32_t stat_mask = st.prog.stat_mask, lut_mask = st.prog.lut_mask;
+    if (lut_mask == 0) return;
+    memset(st.hist, 0, sizeof st.hist);
+    st.suml[0] = st.suml[1] = 0;
     for (int j = 0; j < 2; ++j) {
-        int kind = st.op[j].kind;
-        if (kind_needs_hist(kind) || kind_needs_mean(kind)) {
+        if (!((lut_mask >> j) & 1u)) continue;
+        if ((stat_mask >> j) & 1u) {
             Ctx c = make_ctx(raw, H, W, st);
-            if (j == 0) accumulate<0>(c, kind, st.hist[0], &st.suml[0]);
-            else accumulate<1>(c, kind, st.hist[1], &st.suml[1]);
+            if (j == 0) accumulate<0>(c, st.prog.op[j].kind, st.hist[0], &st.suml[0]);
+            else accumulate<1>(c, st.prog.op[j].kind, st.hist[1], &st.suml[1]);
         }
-        if (kind_uses_lut(kind)) build_lut(st, j, H, W);
+        build_lut(st, j, H, W);
+    }
+    if (st.prog.cls == C_LUT) {
+        for (int i = 0; i < 768; ++i) {
+            uint32_t v = (uint32_t)(i & 255), base = (uint32_t)(i & ~255);
+            if (lut_mask & 1u) v = st.lut[0][base + v];
+            if (lut_mask & 2u) v = st.lut[1][base + v];
+            st.lutc[i] = (uint8_t)v;
+        }
     }
 }
 
-// the kernel's fast path (pointwise-only program, aligned quads): emulated too, so both
-// code paths are checked
-void quad_pixels(const Ctx& c, const Sample& s, bool fast, bool use_zero_box, int out_w, int ox0, int oy,
-                 uint32_t px[4], uint32_t& zmask) {
-    zmask = 0;
-    if (fast) {
-        const int sx0 = (s.flip ? (out_w - 4 - ox0) : ox0) + s.crop_dx;
-        const int ay = oy + s.crop_dy;
-        uint32_t q[4] = {0, 0, 0, 0};
-        const bool inside = (unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H;
-        if (inside) {
-            const uint8_t* b = c.raw + ((size_t)ay * c.W + sx0) * 3u;
-            uint32_t w[3]; memcpy(w, b, 12);
-            q[0] = w[0] & 0xFFFFFFu;
-            q[1] = (w[0] >> 24) | ((w[1] & 0xFFFFu) << 8);
-            q[2] = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
-            q[3] = w[2] >> 8;
-            for (int k = 0; k < 4; ++k)
-                q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
-        }
+struct TailInfo { int crop_dy, crop_dx, flip, zb0, zb1, zb2, zb3; };
+
+TailInfo make_tail(const Prog& g, bool use_zero_box) {
+    TailInfo t; t.crop_dy = g.crop_dy; t.crop_dx = g.crop_dx; t.flip = g.flip;
+    t.zb0 = use_zero_box ? g.zero_box[0] : 0; t.zb1 = use_zero_box ? g.zero_box[1] : 0;
+    t.zb2 = use_zero_box ? g.zero_box[2] : 0; t.zb3 = use_zero_box ? g.zero_box[3] : 0;
+    return t;
+}
+
+uint32_t zero_mask(const TailInfo& t, int ox0, int oy) {
+    if (oy < t.zb0 || oy >= t.zb1) return 0u;
+    uint32_t m = 0;
+    for (int k = 0; k < 4; ++k) m |= (uint32_t)(ox0 + k >= t.zb2 && ox0 + k < t.zb3) << k;
+    return m;
+}
+
+void quad_vec(int cls, const Ctx& c, const uint8_t* lutc, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
+    const int sx0 = (t.flip ? (out_w - 4 - ox0) : ox0) + t.crop_dx;
+    const int ay = oy + t.crop_dy;
+    uint32_t q[4] = {0, 0, 0, 0};
+    if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
+        const uint8_t* b = c.raw + (uint32_t)(ay * c.W + sx0) * 3u;
+        uint32_t w[3]; memcpy(w, b, 12);
+        q[0] = w[0] & 0xFFFFFFu;
+        q[1] = (w[0] >> 24) | ((w[1] & 0xFFFFu) << 8);
+        q[2] = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
+        q[3] = w[2] >> 8;
         for (int k = 0; k < 4; ++k) {
-            px[k] = s.flip ? q[3 - k] : q[k];
-            const int ox = ox0 + k;
-            if (use_zero_box && oy >= s.zero_box[0] && oy < s.zero_box[1] && ox >= s.zero_box[2] && ox < s.zero_box[3])
-                zmask |= 1u << k;
+            if (cls == C_LUT) q[k] = apply_lut(lutc, q[k]);
+            else if (cls == C_POINT) q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
         }
-        return;
     }
+    for (int k = 0; k < 4; ++k) px[k] = t.flip ? q[3 - k] : q[k];
+}
+
+void quad_generic(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
+    const int ay = oy + t.crop_dy;
     for (int k = 0; k < 4; ++k) {
         const int ox = ox0 + k;
         px[k] = 0u;
-        if (ox >= out_w) continue;
-        int ax, ay; bool inside;
-        if (!tail_source(s, use_zero_box, out_w, c.H, c.W, ox, oy, ax, ay, inside)) { zmask |= 1u << k; continue; }
-        if (inside) px[k] = Level<2>::at(c, ax, ay);
+        const int ax = (t.flip ? (out_w - 1 - ox) : ox) + t.crop_dx;
+        if (ox < out_w && (unsigned)ax < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) px[k] = Level<2>::at(c, ax, ay);
     }
 }
 
@@ -140,7 +136,7 @@ extern "C" {
 
 // ops: compiled table [n_sub][n_op][2] (32-byte records); samples/boxes indexed like the kernel's.
 // norm_tab == NULL -> uint8 HWC output, else fp32 NCHW through the exact table.
-// force_generic != 0 disables the aligned fast path (to test both).
+// force_generic != 0 evaluates every image through the generic class (to test both paths).
 int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W, const void* ops_v, int n_sub,
                     int n_op, const void* samples_v, const void* boxes_v, int op_base, int apply_tail, int out_h,
                     int out_w, int use_zero_box, const float* norm_tab, void* out, const int32_t* partner,
@@ -152,23 +148,27 @@ int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W
     const int nsrc = partner ? 2 : 1;
     std::vector<State> st(2);
     const size_t img_bytes = (size_t)H * W * 3;
+    const bool zb = use_zero_box && apply_tail;
     for (int img = 0; img < B; ++img) {
         int src[2] = {first + img, partner ? partner[img] : 0};
-        Ctx c[2]; Sample s[2]; bool fast[2];
-        const bool geom_ok = ((W & 3) == 0) && ((out_w & 3) == 0) && !force_generic;
+        Ctx c[2]; TailInfo t[2]; int cls[2];
         for (int k = 0; k < nsrc; ++k) {
-            load_program(ops, n_op, op_base, apply_tail, H, W, samples[src[k]], boxes + (size_t)src[k] * n_op, st[k]);
+            build_prog(samples[src[k]], boxes + (size_t)src[k] * n_op, ops, n_op, op_base, apply_tail, H, W, out_w,
+                       st[k].prog);
+            if (force_generic) st[k].prog.cls = C_GENERIC;
             prepare(in + img_bytes * src[k], H, W, st[k]);
             c[k] = make_ctx(in + img_bytes * src[k], H, W, st[k]);
-            s[k] = st[k].smp;
-            fast[k] = geom_ok && kind_is_pointwise(c[k].op[0].kind) && kind_is_pointwise(c[k].op[1].kind) &&
-                      ((s[k].crop_dx & 3) == 0);
+            t[k] = make_tail(st[k].prog, zb);
+            cls[k] = st[k].prog.cls;
         }
-        const bool zb = use_zero_box && apply_tail;
         for (int oy = 0; oy < out_h; ++oy)
             for (int ox0 = 0; ox0 < out_w; ox0 += 4) {
                 uint32_t px[2][4], zm[2] = {0, 0};
-                for (int k = 0; k < nsrc; ++k) quad_pixels(c[k], s[k], fast[k], zb, out_w, ox0, oy, px[k], zm[k]);
+                for (int k = 0; k < nsrc; ++k) {
+                    if (cls[k] == C_GENERIC) quad_generic(c[k], t[k], out_w, ox0, oy, px[k]);
+                    else quad_vec(cls[k], c[k], st[k].lutc, t[k], out_w, ox0, oy, px[k]);
+                    zm[k] = zero_mask(t[k], ox0, oy);
+                }
                 const int nvalid = (out_w - ox0) < 4 ? (out_w - ox0) : 4;
                 for (int k = 0; k < nvalid; ++k) {
                     if (!norm_tab) {
@@ -187,6 +187,20 @@ int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W
                     }
                 }
             }
+    }
+    return 0;
+}
+
+// class histogram of a batch (which final-pass specialisation each image takes)
+int faa_emu_classes(const void* ops_v, int n_op, const void* samples_v, const void* boxes_v, int B, int H, int W,
+                    int out_w, int apply_tail, uint8_t* cls_out) {
+    const OpRec* ops = (const OpRec*)ops_v;
+    const Sample* samples = (const Sample*)samples_v;
+    const Box* boxes = (const Box*)boxes_v;
+    for (int i = 0; i < B; ++i) {
+        Prog g;
+        build_prog(samples[i], boxes + (size_t)i * n_op, ops, n_op, 0, apply_tail, H, W, out_w, g);
+        cls_out[i] = g.cls;
     }
     return 0;
 }

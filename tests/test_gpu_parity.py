@@ -264,9 +264,11 @@ def test_full_size_configs(emu, shape, n, pol_name, cutout):
     z = np.zeros(n, dtype=_lib.SAMPLE_DTYPE)
     zb = np.zeros((n, 2), dtype=_lib.BOX_DTYPE)
     ident = augment_batch(off, x, plain_tail, z, zb)
-    ref = ((x.permute(0, 3, 1, 2).float().div(255) - torch.tensor(mean, device="cuda")[None, :, None, None])
-           / torch.tensor(std, device="cuda")[None, :, None, None])
-    assert torch.equal(ident, ref)
+    # torch's CPU ToTensor/Normalize arithmetic (true fp32 division; CUDA torch multiplies by 1/255)
+    tab = torch.from_numpy(exact_norm_table(mean, std))
+    xc = torch.from_numpy(batch).permute(0, 3, 1, 2).long()
+    ref = torch.stack([tab[c][xc[:, c]] for c in range(3)], 1)
+    assert torch.equal(ident.cpu(), ref)
     # fp16 output = fp32 result rounded once
     tail16 = TailSpec(tail.out_size, tail.crop_pad, tail.hflip, mean, std, cutout, torch.float16)
     assert torch.equal(augment_batch(pol, x, tail16, samples, boxes), got.half())
