@@ -29,7 +29,8 @@ assert SAMPLE_DTYPE.itemsize == 16 and BOX_DTYPE.itemsize == 8
 
 class Tail(C.Structure):          # faa_tail_t
     _fields_ = [("out_h", C.c_int32), ("out_w", C.c_int32), ("out_dtype", C.c_int32),
-                ("use_zero_box", C.c_int32), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+                ("use_zero_box", C.c_int32), ("mean", C.c_float * 3), ("std", C.c_float * 3),
+                ("crop_pad", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Rng(C.Structure):           # faa_rng_t

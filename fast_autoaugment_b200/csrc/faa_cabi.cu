@@ -203,6 +203,7 @@ struct faa_policy {
     float norm_host[768];
     // scratch of faa_augment_host
     void* d_progs = nullptr; size_t d_progs_bytes = 0;
+    void* d_order = nullptr;             // int32 [capacity of d_progs in images]
     void* d_in = nullptr; size_t d_in_bytes = 0;
     void* d_out = nullptr; size_t d_out_bytes = 0;
     void* h_in_stage = nullptr; size_t h_in_bytes = 0;
@@ -281,6 +282,7 @@ int faa_policy_destroy(faa_policy_t* p) {
     if (p->d_probs) cudaFree(p->d_probs);
     if (p->d_norm) cudaFree(p->d_norm);
     if (p->d_progs) cudaFree(p->d_progs);
+    if (p->d_order) cudaFree(p->d_order);
     if (p->d_in) cudaFree(p->d_in);
     if (p->d_out) cudaFree(p->d_out);
     if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
@@ -534,9 +536,14 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         std::lock_guard<std::mutex> lk(p->mu);
         size_t need = (size_t)n_all * sizeof(Prog);
         if (p->d_progs_bytes < need) {
-            if (p->d_progs) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(p->d_progs)); p->d_progs = nullptr; p->d_progs_bytes = 0; }
+            if (p->d_progs) {
+                CK(cudaStreamSynchronize(stream));
+                CK(cudaFree(p->d_progs)); CK(cudaFree(p->d_order));
+                p->d_progs = p->d_order = nullptr; p->d_progs_bytes = 0;
+            }
             need = need < 65536 ? 65536 : need * 2;
             CK(cudaMalloc(&p->d_progs, need));
+            CK(cudaMalloc(&p->d_order, need / sizeof(Prog) * sizeof(int32_t) + 16));
             p->d_progs_bytes = need;
         }
     }
@@ -545,6 +552,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     R.ops = d_ops; R.probs = p->d_probs;
     R.samples = reinterpret_cast<const Sample*>(d_samples); R.boxes = reinterpret_cast<const Box*>(d_boxes);
     R.progs = reinterpret_cast<Prog*>(p->d_progs);
+    R.order = d_partner ? nullptr : reinterpret_cast<int32_t*>(p->d_order);
     if (rng) memcpy(&R.rng, rng, sizeof(RngCfg));
     R.first = d_partner ? 0 : first; R.n = d_partner ? n_all : batch;
     R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
@@ -561,6 +569,18 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
     P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
+    P.order = d_partner ? nullptr : reinterpret_cast<const int32_t*>(p->d_order);
+    // TMA band staging needs 16-byte aligned image bases and a band that fits shared memory
+    // (crop_pad only sizes the staged band; rows outside it are read from global memory)
+    P.crop_pad = tail->crop_pad > 0 ? tail->crop_pad : 0;
+    if (rng && rng->crop_pad > P.crop_pad) P.crop_pad = rng->crop_pad;
+    if (P.crop_pad > h) P.crop_pad = h;
+    P.band_cap = (int32_t)band_capacity(P.bands, h, w, tail->out_h, P.crop_pad);
+    const size_t img_bytes = (size_t)h * w * 3;
+    const int nsrc = d_partner ? 2 : 1;
+    static const bool stage_off = [] { const char* e = getenv("FAA_STAGE"); return e && e[0] == '0'; }();
+    P.stage = (!stage_off && img_bytes % 16 == 0 && ((uintptr_t)d_in_all % 16) == 0 &&
+               (size_t)P.band_cap * nsrc <= 150 * 1024) ? 1 : 0;
     CK(launch_augment(P, tail->out_dtype, use_tab, stream));
     g_launches++;
     return FAA_OK;

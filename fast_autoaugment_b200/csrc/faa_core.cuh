@@ -140,7 +140,9 @@ FAA_HD uint32_t color_px(uint32_t p, float alpha, bool clip) {      // augmentat
 
 // ------------------------------------------------------------ image context --
 struct Ctx {
-    const uint8_t* raw;      // this image, uint8 HWC
+    const uint8_t* raw;      // this image, uint8 HWC (global memory)
+    const uint8_t* sraw;     // TMA-staged copy of bytes [s_lo, s_lo + s_len) of the image (shared memory)
+    uint32_t s_lo, s_len2;   // s_len2 = staged length - 2 (0 when nothing is staged)
     int H, W;
     OpRec op[2];             // the two fused op slots (K_NONE when not applied)
     Box box[2];              // clipped inclusive Cutout boxes (valid when op[j].kind==K_CUTOUT)
@@ -148,7 +150,13 @@ struct Ctx {
 };
 
 FAA_HD uint32_t load_raw(const Ctx& c, int x, int y) {
-    const uint8_t* p = c.raw + (uint32_t)(y * c.W + x) * 3u;      // H, W <= 8192: fits 32 bits
+    const uint32_t off = (uint32_t)(y * c.W + x) * 3u;            // H, W <= 8192: fits 32 bits
+    const uint32_t rel = off - c.s_lo;
+    if (rel < c.s_len2) {                                         // inside the staged row band
+        const uint8_t* p = c.sraw + rel;
+        return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    }
+    const uint8_t* p = c.raw + off;
 #if defined(__CUDA_ARCH__)
     return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
 #else
@@ -437,6 +445,21 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
     }
     const bool aligned = ((W & 3) == 0) && ((out_w & 3) == 0) && ((s.crop_dx & 3) == 0);
     g.cls = !aligned || !all_point ? C_GENERIC : !any ? C_PLAIN : all_lut ? C_LUT : C_POINT;
+}
+
+// Rough relative cost of an image (per-pixel work units) - only used to schedule the
+// expensive images first (longest-processing-time order); never affects results.
+FAA_HD uint32_t op_unit_cost(int k) {
+    return k == K_NONE ? 0u : k == K_SHARPNESS ? 10u : (k == K_AFFINE || k == K_SHIFT) ? 3u : k == K_COLOR ? 3u : 1u;
+}
+FAA_HD uint32_t prog_cost(const Prog& g) {
+    const int k0 = g.op[0].kind, k1 = g.op[1].kind;
+    uint32_t c0 = op_unit_cost(k0), c1 = op_unit_cost(k1);
+    uint32_t chain = (k1 == K_SHARPNESS) ? c1 + 9u * c0 : c0 + c1;      // Sharpness re-evaluates 9 taps below it
+    uint32_t cost = 2u + chain + (g.cls == C_GENERIC ? 2u : 0u);
+    if (g.stat_mask & 1u) cost += 2u;                                    // extra pass over the raw band
+    if (g.stat_mask & 2u) cost += 2u + c0;                               // extra pass evaluating op 0
+    return cost;
 }
 
 }  // namespace faa

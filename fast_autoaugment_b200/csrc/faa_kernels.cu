@@ -1,18 +1,23 @@
 // faa_kernels.cu - sm_100a kernels of the augmentation hot path.
 //
 // Two launches per batch:
-//   faa_resolve_kernel   one THREAD per image: per-sample decisions (given records, or drawn
-//                        with Philox4x32-10 keyed by (seed, global sample index)) -> a 96-byte
+//   faa_resolve_kernel   ONE block: per-sample decisions (given records, or drawn with
+//                        Philox4x32-10 keyed by (seed, global sample index)) -> a 96-byte
 //                        per-image program: the two applied op records, clipped Cutout boxes,
-//                        crop / flip / zero-box, and the evaluation CLASS of the image.
+//                        crop / flip / zero-box and the evaluation CLASS of the image; then a
+//                        counting sort of the images by estimated cost, so the pixel kernel
+//                        starts the expensive images first (LPT order, no tail).
 //   faa_augment_kernel   one thread-block CLUSTER per image, one CTA per row band
 //                        (cluster dims (bands,1,1), grid (bands, batch)):
+//     0. thread 0 stages the CTA's row band (+1 halo row each side) of the raw uint8 HWC image
+//        into shared memory with ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier); all pixel
+//        reads below hit shared memory when they fall inside the band and global/L2 otherwise;
 //     1. ops that need whole-image statistics (AutoContrast / Equalize histogram, Contrast
 //        mean luma): each CTA scans its band of the intermediate image, partial statistics are
 //        reduced across the cluster through distributed shared memory, every CTA builds the
 //        op's 3x256-byte LUT; LUT-only programs are composed into ONE LUT;
 //     2. the CTA streams its band of the OUTPUT with the loop specialised for the image's class:
-//          PLAIN   12-byte vector loads -> normalise -> 8-byte plane stores
+//          PLAIN   12-byte vector reads -> normalise -> 8-byte plane stores
 //          LUT     + one composed per-channel LUT lookup
 //          POINT   + pointwise ops in registers (Color, Cutout, LUTs)
 //          GENERIC tail index map (zero box, flip, crop) -> lazy evaluation of the op chain
@@ -35,6 +40,7 @@ namespace cg = cooperative_groups;
 namespace faa {
 
 constexpr int kThreads = 256;
+constexpr int kCostBuckets = 8;
 
 struct __align__(16) ImgState {
     Prog prog;                  // 96 B
@@ -53,38 +59,104 @@ struct FastDiv {
 };
 
 // ---------------------------------------------------------------------------------------
-__global__ void faa_resolve_kernel(const __grid_constant__ ResolveParams P) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n) return;
-    const int i = P.first + t;
-    Sample s;
-    Box bx[8];
-    if (P.samples != nullptr) {
-        s = P.samples[i];
-        for (int j = 0; j < P.n_op; ++j) {
-            if (P.boxes != nullptr) bx[j] = P.boxes[(size_t)i * P.n_op + j];
-            else { bx[j].x0 = bx[j].y0 = 0; bx[j].x1 = bx[j].y1 = -1; }
+// launch 1
+__device__ __forceinline__ int cost_bucket(uint32_t cost) {     // 0 = most expensive
+    int b = kCostBuckets - 1;
+    uint32_t th = 4u;
+    while (b > 0 && cost >= th) { --b; th *= 2u; }
+    return b;
+}
+
+__global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant__ ResolveParams P) {
+    __shared__ int s_count[kCostBuckets], s_base[kCostBuckets];
+    if (threadIdx.x < kCostBuckets) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < P.n; t += blockDim.x) {
+        const int i = P.first + t;
+        Sample s;
+        Box bx[8];
+        if (P.samples != nullptr) {
+            s = P.samples[i];
+            for (int j = 0; j < P.n_op; ++j) {
+                if (P.boxes != nullptr) bx[j] = P.boxes[(size_t)i * P.n_op + j];
+                else { bx[j].x0 = bx[j].y0 = 0; bx[j].x1 = bx[j].y1 = -1; }
+            }
+        } else {
+            philox_sample(P.rng, P.rng.first_index + (uint64_t)i, P.ops, P.probs, P.n_sub, P.n_op, P.H, P.W,
+                          P.out_h, P.out_w, s, bx);
         }
-    } else {
-        philox_sample(P.rng, P.rng.first_index + (uint64_t)i, P.ops, P.probs, P.n_sub, P.n_op, P.H, P.W,
-                      P.out_h, P.out_w, s, bx);
+        if (P.progs != nullptr) {
+            Prog g;
+            build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, g);
+            g.pad[0] = (uint8_t)cost_bucket(prog_cost(g));
+            P.progs[i] = g;
+            atomicAdd(&s_count[g.pad[0]], 1);
+        }
+        if (P.samples_out != nullptr) P.samples_out[i] = s;
+        if (P.boxes_out != nullptr)
+            for (int j = 0; j < P.n_op; ++j) P.boxes_out[(size_t)i * P.n_op + j] = bx[j];
     }
-    if (P.progs != nullptr) {
-        Prog g;
-        build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, g);
-        P.progs[i] = g;
+    if (P.order == nullptr || P.progs == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < kCostBuckets; ++b) { s_base[b] = acc; acc += s_count[b]; s_count[b] = 0; }
     }
-    if (P.samples_out != nullptr) P.samples_out[i] = s;
-    if (P.boxes_out != nullptr)
-        for (int j = 0; j < P.n_op; ++j) P.boxes_out[(size_t)i * P.n_op + j] = bx[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < P.n; t += blockDim.x) {        // scheduling order only: any order is correct
+        const int b = P.progs[P.first + t].pad[0];
+        P.order[P.first + s_base[b] + atomicAdd(&s_count[b], 1)] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ Ctx make_ctx(const uint8_t* raw, int H, int W, const ImgState& st) {
+// TMA 1-D bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_stage(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+    const uint32_t b = smem_u32(bar), d = smem_u32(dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    const uint32_t b = smem_u32(bar);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(b), "r"(phase) : "memory");
+    }
+}
+
+// the byte range of image rows a CTA may touch through the band-local paths
+__host__ __device__ inline void band_range(int band, int bands, int H, int W, int out_h, int crop_pad,
+                                            uint32_t img_bytes, uint32_t& lo, uint32_t& len) {
+    const int y0 = (int)(((long long)band * H) / bands), y1 = (int)(((long long)(band + 1) * H) / bands);
+    const int oy0 = (int)(((long long)band * out_h) / bands), oy1 = (int)(((long long)(band + 1) * out_h) / bands);
+    int r0 = (y0 < oy0 - crop_pad ? y0 : oy0 - crop_pad) - 1;
+    int r1 = (y1 > oy1 + crop_pad ? y1 : oy1 + crop_pad) + 1;
+    if (r0 < 0) r0 = 0;
+    if (r1 > H) r1 = H;
+    if (r1 <= r0) { lo = 0; len = 0; return; }
+    const uint32_t row = (uint32_t)W * 3u;
+    lo = ((uint32_t)r0 * row) & ~15u;
+    uint32_t hi = ((uint32_t)r1 * row + 15u) & ~15u;
+    if (hi > img_bytes) hi = img_bytes;
+    len = hi - lo;
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ Ctx make_ctx(const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo, uint32_t s_len,
+                                        int H, int W, const ImgState& st, bool full) {
     Ctx c;
-    c.raw = raw; c.H = H; c.W = W;
-    c.op[0] = st.prog.op[0]; c.op[1] = st.prog.op[1];
-    c.box[0] = st.prog.box[0]; c.box[1] = st.prog.box[1];
+    c.raw = raw; c.sraw = sraw; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u; c.H = H; c.W = W;
+    if (full) {
+        c.op[0] = st.prog.op[0]; c.op[1] = st.prog.op[1];
+        c.box[0] = st.prog.box[0]; c.box[1] = st.prog.box[1];
+    }
     c.lut[0] = st.lut[0]; c.lut[1] = st.lut[1];
     return c;
 }
@@ -96,18 +168,31 @@ __device__ __forceinline__ void unpack12(uint32_t w0, uint32_t w1, uint32_t w2, 
     q[3] = w2 >> 8;
 }
 
+// 12 contiguous, 4-byte aligned bytes of the raw image at byte offset `off`
+__device__ __forceinline__ void load12(const Ctx& c, uint32_t off, uint32_t q[4]) {
+    const uint32_t rel = off - c.s_lo;
+    const uint32_t lim = c.s_len2 > 9u ? c.s_len2 - 9u : 0u;
+    if (rel < lim) {                   // rel + 11 < staged length (no unsigned wrap)
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(c.sraw + rel);
+        unpack12(w[0], w[1], w[2], q);
+    } else {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(c.raw + off);
+        unpack12(__ldg(w), __ldg(w + 1), __ldg(w + 2), q);
+    }
+}
+
 // statistics of the image in front of slot L (0 or 1) over rows [y0, y1)
 template <int L>
 __device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_t* hist, unsigned long long* suml) {
     const bool mean = kind == K_CONTRAST;
     uint32_t local = 0;
     if (L == 0 && (c.W & 3) == 0) {
-        // raw image: 4 pixels per thread from three aligned 32-bit loads
+        // raw image: 4 pixels per thread from 12 aligned bytes
         const uint32_t nq = (uint32_t)(y1 - y0) * (uint32_t)c.W / 4u;
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(c.raw + (uint32_t)y0 * (uint32_t)c.W * 3u);
+        const uint32_t base = (uint32_t)y0 * (uint32_t)c.W * 3u;
         for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
             uint32_t q[4];
-            unpack12(__ldg(base + 3u * i), __ldg(base + 3u * i + 1), __ldg(base + 3u * i + 2), q);
+            load12(c, base + 12u * i, q);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (mean) local += luma_of(q[k]);
@@ -178,8 +263,10 @@ __device__ void build_slot_lut(int bands, uint32_t n_pixels, ImgState& st, int j
     __syncthreads();
 }
 
-// everything before the final pass for one source image
-__device__ bool prepare_image(const AugParams& P, const uint8_t* raw, int band, ImgState& st, cg::cluster_group& cluster) {
+// everything before the final pass for one source image; returns true when the cluster
+// exchanged statistics (=> peers may still be reading this CTA's shared memory)
+__device__ bool prepare_image(const AugParams& P, const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo,
+                              uint32_t s_len, int band, ImgState& st, cg::cluster_group& cluster) {
     const uint32_t stat_mask = st.prog.stat_mask, lut_mask = st.prog.lut_mask;
     if (lut_mask == 0) return false;
     const int y0 = (int)(((long long)band * P.H) / P.bands);
@@ -193,7 +280,7 @@ __device__ bool prepare_image(const AugParams& P, const uint8_t* raw, int band, 
     for (int j = 0; j < 2; ++j) {
         if (!((lut_mask >> j) & 1u)) continue;
         if ((stat_mask >> j) & 1u) {
-            Ctx c = make_ctx(raw, P.H, P.W, st);
+            Ctx c = make_ctx(raw, sraw, s_lo, s_len, P.H, P.W, st, true);
             const int kind = st.prog.op[j].kind;
             if (j == 0) accumulate_stats<0>(c, kind, y0, y1, st.hist[0], &st.suml[0]);
             else        accumulate_stats<1>(c, kind, y0, y1, st.hist[1], &st.suml[1]);
@@ -244,8 +331,7 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
     const int ay = oy + t.crop_dy;
     uint32_t q[4] = {0u, 0u, 0u, 0u};
     if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(c.raw + (uint32_t)(ay * c.W + sx0) * 3u);
-        unpack12(__ldg(w), __ldg(w + 1), __ldg(w + 2), q);
+        load12(c, (uint32_t)(ay * c.W + sx0) * 3u, q);
         if (CLS == C_LUT) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) q[k] = apply_lut(lutc, q[k]);
@@ -342,7 +428,8 @@ __device__ __forceinline__ void emit_quad(const AugParams& P, const float* s_nor
 
 template <int OUT, bool TAB, int CLS>
 __device__ __forceinline__ void final_pass(const AugParams& P, const float* s_norm, const ImgState& st,
-                                           const uint8_t* raw, void* out_img, int band) {
+                                           const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo, uint32_t s_len,
+                                           void* out_img, int band) {
     const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
     const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
@@ -350,9 +437,7 @@ __device__ __forceinline__ void final_pass(const AugParams& P, const float* s_no
     FastDiv dq; dq.init(qpr);
     const bool vec = (P.out_w & 3) == 0;
     const TailInfo t = make_tail(P, st.prog);
-    Ctx c;
-    if (CLS == C_POINT || CLS == C_GENERIC) c = make_ctx(raw, P.H, P.W, st);
-    else { c.raw = raw; c.H = P.H; c.W = P.W; }
+    const Ctx c = make_ctx(raw, sraw, s_lo, s_len, P.H, P.W, st, CLS == C_POINT || CLS == C_GENERIC);
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
         const uint32_t r = dq.div(q);
         const int ox0 = (int)(q - r * qpr) * 4;
@@ -366,8 +451,8 @@ __device__ __forceinline__ void final_pass(const AugParams& P, const float* s_no
 
 // two sources mixed in fp32 (fused Mixup): class dispatch per quad, both contexts live
 template <int OUT, bool TAB>
-__device__ void final_pass_mix(const AugParams& P, const float* s_norm, const ImgState* st, const uint8_t* raw0,
-                               const uint8_t* raw1, void* out_img, int band) {
+__device__ void final_pass_mix(const AugParams& P, const float* s_norm, const ImgState* st, const Ctx& c0,
+                               const Ctx& c1, void* out_img, int band) {
     using T = typename OutElem<OUT>::T;
     const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
     const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
@@ -376,7 +461,6 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
     FastDiv dq; dq.init(qpr);
     const bool vec = (P.out_w & 3) == 0;
     const TailInfo t0 = make_tail(P, st[0].prog), t1 = make_tail(P, st[1].prog);
-    const Ctx c0 = make_ctx(raw0, P.H, P.W, st[0]), c1 = make_ctx(raw1, P.H, P.W, st[1]);
     const int cls0 = st[0].prog.cls, cls1 = st[1].prog.cls;
     const uint32_t plane = (uint32_t)P.out_h * (uint32_t)P.out_w;
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
@@ -408,18 +492,31 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
 }
 
 // ---------------------------------------------------------------------------------------
+// launch 2
 template <int OUT, int NSRC, bool TAB>
 __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
+    extern __shared__ __align__(128) uint8_t s_band[];          // NSRC staged row bands
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st[NSRC];
     __shared__ float s_norm[TAB ? 768 : 1];
+    __shared__ __align__(8) uint64_t s_bar[NSRC];
 
     const int band = blockIdx.x;
-    const int img = blockIdx.y;
+    const int img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
     int src_idx[NSRC];
     src_idx[0] = P.first + img;
     if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
 
+    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
+    uint32_t s_lo = 0, s_len = 0;
+    if (P.stage) band_range(band, P.bands, P.H, P.W, P.out_h, P.crop_pad, img_bytes, s_lo, s_len);
+
+    // 0. stage the raw row band(s): one TMA bulk copy each, in flight while the program loads
+    if (threadIdx.x == 0 && s_len) {
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s)
+            tma_stage(&s_bar[s], s_band + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
+    }
     // per-image programs -> shared memory (24 words each)
 #pragma unroll
     for (int s = 0; s < NSRC; ++s)
@@ -429,14 +526,17 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_ker
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     __syncthreads();
+    if (s_len) {
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
+    }
 
-    const size_t img_bytes = (size_t)P.H * (size_t)P.W * 3u;
     const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
-    bool any_stats = prepare_image(P, raw0, band, st[0], cluster);
+    bool any_stats = prepare_image(P, raw0, s_band, s_lo, s_len, band, st[0], cluster);
     const uint8_t* raw1 = raw0;
     if constexpr (NSRC == 2) {
         raw1 = P.in + (size_t)src_idx[1] * img_bytes;
-        any_stats |= prepare_image(P, raw1, band, st[1], cluster);
+        any_stats |= prepare_image(P, raw1, s_band + P.band_cap, s_lo, s_len, band, st[1], cluster);
     }
 
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
@@ -444,13 +544,15 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_ker
 
     if constexpr (NSRC == 1) {
         switch (st[0].prog.cls) {
-        case C_PLAIN: final_pass<OUT, TAB, C_PLAIN>(P, s_norm, st[0], raw0, out_img, band); break;
-        case C_LUT:   final_pass<OUT, TAB, C_LUT>(P, s_norm, st[0], raw0, out_img, band); break;
-        case C_POINT: final_pass<OUT, TAB, C_POINT>(P, s_norm, st[0], raw0, out_img, band); break;
-        default:      final_pass<OUT, TAB, C_GENERIC>(P, s_norm, st[0], raw0, out_img, band); break;
+        case C_PLAIN: final_pass<OUT, TAB, C_PLAIN>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
+        case C_LUT:   final_pass<OUT, TAB, C_LUT>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
+        case C_POINT: final_pass<OUT, TAB, C_POINT>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
+        default:      final_pass<OUT, TAB, C_GENERIC>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
         }
     } else {
-        final_pass_mix<OUT, TAB>(P, s_norm, st, raw0, raw1, out_img, band);
+        const Ctx c0 = make_ctx(raw0, s_band, s_lo, s_len, P.H, P.W, st[0], true);
+        const Ctx c1 = make_ctx(raw1, s_band + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
+        final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
     }
 
     // a CTA must not exit while cluster peers may still read its partial statistics
@@ -482,12 +584,30 @@ int pick_bands(int H, int W, int out_h, int out_w) {
     return b;
 }
 
+uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
+    uint32_t cap = 0;
+    for (int b = 0; b < bands; ++b) {
+        uint32_t lo, len;
+        band_range(b, bands, H, W, out_h, crop_pad, (uint32_t)H * (uint32_t)W * 3u, lo, len);
+        if (len > cap) cap = len;
+    }
+    return (cap + 127u) & ~127u;
+}
+
 template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
+    const size_t dyn = p.stage ? (size_t)p.band_cap * NSRC : 0;
+    static size_t configured = 0;                   // per instantiation
+    if (dyn > configured) {
+        cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        configured = dyn;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -519,7 +639,8 @@ cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaS
 
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
-    faa_resolve_kernel<<<(p.n + 127) / 128, 128, 0, stream>>>(p);
+    int threads = p.n >= 1024 ? 1024 : ((p.n + 31) / 32) * 32;
+    faa_resolve_kernel<<<1, threads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ struct ResolveParams {
     const Sample* samples;      // [n] resolved decisions, or nullptr -> draw with Philox
     const Box* boxes;           // [n][n_op] (may be nullptr when no Cutout box is needed)
     Prog* progs;                // [n] out
+    int32_t* order;             // [n] out: local image indices, most expensive first (optional)
     Sample* samples_out;        // optional [n]
     Box* boxes_out;             // optional [n][n_op]
     RngCfg rng;
@@ -29,11 +30,15 @@ struct AugParams {
     void* out;                  // [B][3][out_h][out_w] OutT  (or [B][out_h][out_w][3] uint8)
     const Prog* progs;          // [n_all]
     const int32_t* partner;     // [B] index into [0, n_all) or nullptr (no mixup)
+    const int32_t* order;       // [n_all] LPT schedule written by the resolve kernel, or nullptr
     const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values
     int32_t B, H, W, out_h, out_w;
     int32_t first;              // index of this launch's image 0 inside the n_all arrays
     int32_t use_zero_box;
     int32_t bands;              // CTAs (== cluster size) per image
+    int32_t stage;              // 1: TMA-stage the raw row band into shared memory
+    int32_t band_cap;           // bytes of dynamic shared memory per staged band
+    int32_t crop_pad;           // max |crop_dy| (RandomCrop padding)
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };
@@ -43,5 +48,6 @@ cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int b
                          int dtype, float lam, float one_minus_lam, cudaStream_t stream);
 
 int pick_bands(int H, int W, int out_h, int out_w);
+uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad);
 
 }  // namespace faa

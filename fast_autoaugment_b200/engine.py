@@ -61,6 +61,7 @@ class TailSpec:
         t.out_h, t.out_w = int(oh), int(ow)
         t.out_dtype = _DTYPES[self.out_dtype]
         t.use_zero_box = 1 if self.cutout > 0 else 0
+        t.crop_pad = int(self.crop_pad)
         for i in range(3):
             t.mean[i] = float(self.mean[i])
             t.std[i] = float(self.std[i])

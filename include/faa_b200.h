@@ -81,6 +81,8 @@ typedef struct faa_tail {
     int32_t out_dtype;        /* enum faa_dtype; FAA_U8_HWC skips ToTensor/Normalize         */
     int32_t use_zero_box;     /* apply faa_sample.zero_box (CutoutDefault)                   */
     float   mean[3], std[3];  /* Normalize                                                  */
+    int32_t crop_pad;         /* RandomCrop padding = bound on |crop_dy| (sizes the staged band; a hint) */
+    int32_t reserved;
 } faa_tail_t;
 
 /* parameters of the device-side (Philox4x32-10) sampler: the distribution of every draw

@@ -29,7 +29,7 @@ struct State {
 };
 
 Ctx make_ctx(const uint8_t* raw, int H, int W, const State& st) {
-    Ctx c; c.raw = raw; c.H = H; c.W = W;
+    Ctx c; c.raw = raw; c.sraw = nullptr; c.s_lo = 0; c.s_len2 = 0; c.H = H; c.W = W;   // no staged band on the host
     c.op[0] = st.prog.op[0]; c.op[1] = st.prog.op[1]; c.box[0] = st.prog.box[0]; c.box[1] = st.prog.box[1];
     c.lut[0] = st.lut[0]; c.lut[1] = st.lut[1];
     return c;
