@@ -547,27 +547,13 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             p->d_progs_bytes = need;
         }
     }
-    // launch 1: decisions -> programs (the whole pool when partners may be anywhere in it)
-    ResolveParams R; memset(&R, 0, sizeof R);
-    R.ops = d_ops; R.probs = p->d_probs;
-    R.samples = reinterpret_cast<const Sample*>(d_samples); R.boxes = reinterpret_cast<const Box*>(d_boxes);
-    R.progs = reinterpret_cast<Prog*>(p->d_progs);
-    R.order = d_partner ? nullptr : reinterpret_cast<int32_t*>(p->d_order);
-    if (rng) memcpy(&R.rng, rng, sizeof(RngCfg));
-    R.first = d_partner ? 0 : first; R.n = d_partner ? n_all : batch;
-    R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
-    R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = op_base; R.apply_tail = apply_tail;
-    CK(launch_resolve(R, stream));
-    g_launches++;
-    // launch 2: pixels
+    // geometry of the pixel launch (needed by the resolve step: allow_mat)
     AugParams P; memset(&P, 0, sizeof P);
     P.in = d_in_all; P.out = d_out; P.progs = reinterpret_cast<const Prog*>(p->d_progs);
     P.partner = d_partner;
     P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.first = first;
     P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
     P.lam = lam; P.one_minus_lam = oml;
-    bool use_tab = false;
-    if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
     P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
     P.order = d_partner ? nullptr : reinterpret_cast<const int32_t*>(p->d_order);
     // TMA band staging needs 16-byte aligned image bases and a band that fits shared memory
@@ -579,8 +565,35 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const size_t img_bytes = (size_t)h * w * 3;
     const int nsrc = d_partner ? 2 : 1;
     static const bool stage_off = [] { const char* e = getenv("FAA_STAGE"); return e && e[0] == '0'; }();
+    static const bool mat_off = [] { const char* e = getenv("FAA_MAT"); return e && e[0] == '0'; }();
+    static const bool pdl_off = [] { const char* e = getenv("FAA_PDL"); return e && e[0] == '0'; }();
     P.stage = (!stage_off && img_bytes % 16 == 0 && ((uintptr_t)d_in_all % 16) == 0 &&
                (size_t)P.band_cap * nsrc <= 150 * 1024) ? 1 : 0;
+    if (!P.stage) P.band_cap = 0;
+    // materialisation chunk: as many rows as fit ~16 KB, at least 3 (single-source launches only)
+    {
+        const int pitch = w * 3;
+        int rows = 16384 / pitch;
+        if (rows > h + 2) rows = h + 2;
+        P.mat_cap = (!mat_off && !d_partner && rows >= 3) ? ((rows * pitch + 15) & ~15) : 0;
+    }
+    P.pdl = pdl_off ? 0 : 1;
+    // launch 1: decisions -> programs (the whole pool when partners may be anywhere in it)
+    ResolveParams R; memset(&R, 0, sizeof R);
+    R.ops = d_ops; R.probs = p->d_probs;
+    R.samples = reinterpret_cast<const Sample*>(d_samples); R.boxes = reinterpret_cast<const Box*>(d_boxes);
+    R.progs = reinterpret_cast<Prog*>(p->d_progs);
+    R.order = d_partner ? nullptr : reinterpret_cast<int32_t*>(p->d_order);
+    if (rng) memcpy(&R.rng, rng, sizeof(RngCfg));
+    R.first = d_partner ? 0 : first; R.n = d_partner ? n_all : batch;
+    R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
+    R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = op_base; R.apply_tail = apply_tail;
+    R.allow_mat = P.mat_cap > 0 ? 1 : 0;
+    bool use_tab = false;
+    if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
+    CK(launch_resolve(R, stream));
+    g_launches++;
+    // launch 2: pixels
     CK(launch_augment(P, tail->out_dtype, use_tab, stream));
     g_launches++;
     return FAA_OK;

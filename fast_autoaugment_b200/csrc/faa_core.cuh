@@ -392,6 +392,54 @@ FAA_HD void philox_sample(const RngCfg& r, uint64_t index, const OpRec* ops, con
 FAA_HD uint32_t recip32(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
 FAA_HD uint32_t fastdiv(uint32_t q, uint32_t rcp) { return umulhi32(q, rcp); }
 
+// ------------------------------------------------ vectorised 3x3 Sharpness --
+// Four consecutive output pixels (x0 % 4 == 0) of Sharpness (augmentations.py:112-114) from
+// three source rows.  rm/r0/rp point at pixel x0 of rows y-1, y, y+1 (any address space, 4-byte
+// aligned); has_l / has_r tell whether columns x0-1 / x0+4 exist; edge bits mark pixels of the
+// quad that lie on the image border (copied unchanged, like Pillow's filter).  The 3x3 sums are
+// built from per-column sums with R|B packed in one register (16-bit lanes) and G in another.
+FAA_HD uint32_t ld32(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const uint32_t*>(p);
+#else
+    uint32_t v; __builtin_memcpy(&v, p, 4); return v;
+#endif
+}
+FAA_HD void row6(const uint8_t* r, bool has_l, bool has_r, uint32_t px[6]) {
+    uint32_t w0 = ld32(r), w1 = ld32(r + 4), w2 = ld32(r + 8);
+    px[0] = has_l ? (ld32(r - 4) >> 8) : 0u;
+    px[1] = w0 & 0xFFFFFFu;
+    px[2] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8);
+    px[3] = (w1 >> 16) | ((w2 & 0xFFu) << 16);
+    px[4] = w2 >> 8;
+    px[5] = has_r ? (ld32(r + 12) & 0xFFFFFFu) : 0u;
+}
+FAA_HD void sharp_quad(const uint8_t* rm, const uint8_t* r0, const uint8_t* rp, bool has_l, bool has_r,
+                       bool row_is_border, bool left_is_border, bool right_is_border, float alpha, bool clip,
+                       uint32_t out[4]) {
+    uint32_t c[6];
+    row6(r0, has_l, has_r, c);
+    if (row_is_border) { out[0] = c[1]; out[1] = c[2]; out[2] = c[3]; out[3] = c[4]; return; }
+    uint32_t a[6], b[6];
+    row6(rm, has_l, has_r, a);
+    row6(rp, has_l, has_r, b);
+    uint32_t rb[6], g[6];
+    for (int i = 0; i < 6; ++i) {
+        rb[i] = (a[i] & 0xFF00FFu) + (c[i] & 0xFF00FFu) + (b[i] & 0xFF00FFu);
+        g[i] = ((a[i] >> 8) & 0xFFu) + ((c[i] >> 8) & 0xFFu) + ((b[i] >> 8) & 0xFFu);
+    }
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t ctr = c[k + 1];
+        if ((k == 0 && left_is_border) || (k == 3 && right_is_border)) { out[k] = ctr; continue; }
+        uint32_t srb = rb[k] + rb[k + 1] + rb[k + 2] + 4u * (ctr & 0xFF00FFu);
+        uint32_t sg = g[k] + g[k + 1] + g[k + 2] + 4u * ((ctr >> 8) & 0xFFu);
+        uint32_t dr = (2u * (srb & 0xFFFFu) + 13u) / 26u, db = (2u * (srb >> 16) + 13u) / 26u;
+        uint32_t dg = (2u * sg + 13u) / 26u;                       // [1 1 1;1 5 1;1 1 1]/13, round half up
+        out[k] = blend_u8(dr, ctr & 255u, alpha, clip) | (blend_u8(dg, (ctr >> 8) & 255u, alpha, clip) << 8) |
+                 (blend_u8(db, (ctr >> 16) & 255u, alpha, clip) << 16);
+    }
+}
+
 // ------------------------------------------------------- per-image program --
 // What the resolve step hands to the pixel kernel for one image: the two applied op records,
 // clipped Cutout boxes, the tail decisions and the evaluation class of the final pass.
@@ -399,7 +447,10 @@ enum ProgClass : uint8_t {
     C_PLAIN = 0,     // no op applied, aligned: 12-byte vector loads straight to the store
     C_LUT = 1,       // every applied op is a per-channel LUT (static / hist / blend-with-const), aligned
     C_POINT = 2,     // pointwise incl. Color / Cutout, aligned
-    C_GENERIC = 3    // geometric ops, Sharpness, or unaligned rows: per-pixel lazy evaluation
+    C_GENERIC = 3,   // geometric ops, unaligned rows, ...: per-pixel lazy evaluation of the chain
+    C_SHARP = 4,     // Sharpness on the raw image then a pointwise op, aligned: vectorised 3x3
+    C_MAT = 5        // op0 then (Sharpness | statistics op): op0's output is materialised chunk-wise in
+                     // shared memory and op1 runs on it as a single-op program of class `cls2`
 };
 
 struct Prog {        // 96 bytes
@@ -409,20 +460,22 @@ struct Prog {        // 96 bytes
     int8_t crop_dy, crop_dx; uint8_t flip; uint8_t cls;
     uint8_t stat_mask;           // bit j: slot j needs whole-image statistics
     uint8_t lut_mask;            // bit j: slot j is evaluated through a 3x256 LUT
-    uint8_t pad[2];
+    uint8_t bucket;              // scheduling cost bucket (0 = most expensive)
+    uint8_t cls2;                // C_MAT: class of the op1-only program run on the materialised chunk
 };
 
 FAA_HD bool kind_is_lutlike(int k) { return k == K_NONE || kind_uses_lut(k); }
 
 // Sample + boxes -> Prog.  ops: compiled table [n_sub][n_op][2]; boxes: this sample's n_op boxes.
+// allow_mat: the launch has a materialisation buffer of at least 3 rows (single-source launches).
 FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, int n_op, int op_base,
-                       int apply_tail, int H, int W, int out_w, Prog& g) {
+                       int apply_tail, int H, int W, int out_w, int allow_mat, Prog& g) {
     Sample s = s_in;
     if (!apply_tail) { s.crop_dx = s.crop_dy = 0; s.flip = 0; s.zero_box[0] = s.zero_box[1] = s.zero_box[2] = s.zero_box[3] = 0; }
     g.crop_dy = s.crop_dy; g.crop_dx = s.crop_dx; g.flip = s.flip;
     for (int i = 0; i < 4; ++i) g.zero_box[i] = s.zero_box[i];
-    g.stat_mask = 0; g.lut_mask = 0; g.pad[0] = g.pad[1] = 0;
-    bool all_point = true, all_lut = true, any = false;
+    g.stat_mask = 0; g.lut_mask = 0; g.bucket = 0; g.cls2 = C_GENERIC;
+    int n = 0;
     for (int j = 0; j < 2; ++j) {
         int jj = op_base + j;
         OpRec o; o.kind = K_NONE; o.a[0] = o.a[1] = o.a[2] = o.a[3] = o.a[4] = o.a[5] = 0; o.draw = 0;
@@ -436,26 +489,44 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
             if (b.y1 > H - 1) b.y1 = (int16_t)(H - 1);
             if (b.x1 < b.x0 || b.y1 < b.y0) o.kind = K_NONE;
         }
-        g.op[j] = o; g.box[j] = b;
-        if (kind_needs_hist(o.kind) || kind_needs_mean(o.kind)) g.stat_mask |= (uint8_t)(1u << j);
-        if (kind_uses_lut(o.kind)) g.lut_mask |= (uint8_t)(1u << j);
-        all_point = all_point && kind_is_pointwise(o.kind);
-        all_lut = all_lut && kind_is_lutlike(o.kind);
-        any = any || o.kind != K_NONE;
+        if (o.kind != K_NONE) { g.op[n] = o; g.box[n] = b; ++n; }   // applied ops are compacted to the front
     }
+    for (int j = n; j < 2; ++j) {
+        g.op[j].kind = K_NONE; g.op[j].a[0] = g.op[j].a[1] = g.op[j].a[2] = g.op[j].a[3] = g.op[j].a[4] = g.op[j].a[5] = 0;
+        g.op[j].draw = 0;
+        g.box[j].x0 = g.box[j].y0 = 0; g.box[j].x1 = g.box[j].y1 = -1;
+    }
+    bool all_point = true, all_lut = true;
+    for (int j = 0; j < 2; ++j) {
+        const int k = g.op[j].kind;
+        if (kind_needs_hist(k) || kind_needs_mean(k)) g.stat_mask |= (uint8_t)(1u << j);
+        if (kind_uses_lut(k)) g.lut_mask |= (uint8_t)(1u << j);
+        all_point = all_point && kind_is_pointwise(k);
+        all_lut = all_lut && kind_is_lutlike(k);
+    }
+    const int k0 = g.op[0].kind, k1 = g.op[1].kind;
     const bool aligned = ((W & 3) == 0) && ((out_w & 3) == 0) && ((s.crop_dx & 3) == 0);
-    g.cls = !aligned || !all_point ? C_GENERIC : !any ? C_PLAIN : all_lut ? C_LUT : C_POINT;
+    const bool k1_stat = kind_needs_hist(k1) || kind_needs_mean(k1);
+    if (allow_mat && k0 != K_NONE && (k1 == K_SHARPNESS || k1_stat)) {
+        g.cls = C_MAT;
+        g.cls2 = !aligned ? C_GENERIC : (k1 == K_SHARPNESS ? C_SHARP : C_LUT);
+    } else if (!aligned) g.cls = C_GENERIC;
+    else if (all_point) g.cls = n == 0 ? C_PLAIN : all_lut ? C_LUT : C_POINT;
+    else if (k0 == K_SHARPNESS && kind_is_pointwise(k1)) g.cls = C_SHARP;
+    else g.cls = C_GENERIC;
 }
 
 // Rough relative cost of an image (per-pixel work units) - only used to schedule the
 // expensive images first (longest-processing-time order); never affects results.
 FAA_HD uint32_t op_unit_cost(int k) {
-    return k == K_NONE ? 0u : k == K_SHARPNESS ? 10u : (k == K_AFFINE || k == K_SHIFT) ? 3u : k == K_COLOR ? 3u : 1u;
+    return k == K_NONE ? 0u : k == K_SHARPNESS ? 12u : (k == K_AFFINE || k == K_SHIFT) ? 4u : k == K_COLOR ? 3u : 1u;
 }
 FAA_HD uint32_t prog_cost(const Prog& g) {
     const int k0 = g.op[0].kind, k1 = g.op[1].kind;
     uint32_t c0 = op_unit_cost(k0), c1 = op_unit_cost(k1);
-    uint32_t chain = (k1 == K_SHARPNESS) ? c1 + 9u * c0 : c0 + c1;      // Sharpness re-evaluates 9 taps below it
+    if (g.cls == C_SHARP) c0 = 5u;
+    if (g.cls == C_MAT && g.cls2 == C_SHARP) c1 = 5u;
+    uint32_t chain = (k1 == K_SHARPNESS && g.cls != C_MAT) ? c1 + 9u * c0 : c0 + c1;   // lazy Sharpness: 9 taps below it
     uint32_t cost = 2u + chain + (g.cls == C_GENERIC ? 2u : 0u);
     if (g.stat_mask & 1u) cost += 2u;                                    // extra pass over the raw band
     if (g.stat_mask & 2u) cost += 2u + c0;                               // extra pass evaluating op 0

@@ -69,6 +69,8 @@ __device__ __forceinline__ int cost_bucket(uint32_t cost) {     // 0 = most expe
 
 __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant__ ResolveParams P) {
     __shared__ int s_count[kCostBuckets], s_base[kCostBuckets];
+    // let the dependent pixel kernel start launching (its prologue overlaps this kernel)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x < kCostBuckets) s_count[threadIdx.x] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {
@@ -87,10 +89,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
         }
         if (P.progs != nullptr) {
             Prog g;
-            build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, g);
-            g.pad[0] = (uint8_t)cost_bucket(prog_cost(g));
+            build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, P.allow_mat, g);
+            g.bucket = (uint8_t)cost_bucket(prog_cost(g));
             P.progs[i] = g;
-            atomicAdd(&s_count[g.pad[0]], 1);
+            atomicAdd(&s_count[g.bucket], 1);
         }
         if (P.samples_out != nullptr) P.samples_out[i] = s;
         if (P.boxes_out != nullptr)
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
     }
     __syncthreads();
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {        // scheduling order only: any order is correct
-        const int b = P.progs[P.first + t].pad[0];
+        const int b = P.progs[P.first + t].bucket;
         P.order[P.first + s_base[b] + atomicAdd(&s_count[b], 1)] = t;
     }
 }
@@ -168,6 +170,13 @@ __device__ __forceinline__ void unpack12(uint32_t w0, uint32_t w1, uint32_t w2, 
     q[3] = w2 >> 8;
 }
 
+// pointer to byte `off` of the image: the staged copy when [off-4, off+16) is inside it, else global
+__device__ __forceinline__ const uint8_t* src_ptr(const Ctx& c, uint32_t off) {
+    const uint32_t rel = off - c.s_lo;
+    const uint32_t lim = c.s_len2 > 18u ? c.s_len2 - 14u : 0u;          // rel >= 4 and rel + 16 <= staged length
+    return (rel - 4u < lim - 4u) ? c.sraw + rel : c.raw + off;
+}
+
 // 12 contiguous, 4-byte aligned bytes of the raw image at byte offset `off`
 __device__ __forceinline__ void load12(const Ctx& c, uint32_t off, uint32_t q[4]) {
     const uint32_t rel = off - c.s_lo;
@@ -179,6 +188,12 @@ __device__ __forceinline__ void load12(const Ctx& c, uint32_t off, uint32_t q[4]
         const uint32_t* w = reinterpret_cast<const uint32_t*>(c.raw + off);
         unpack12(__ldg(w), __ldg(w + 1), __ldg(w + 2), q);
     }
+}
+
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t p) {
+    atomicAdd(&hist[p & 255u], 1u);
+    atomicAdd(&hist[256u + ((p >> 8) & 255u)], 1u);
+    atomicAdd(&hist[512u + (p >> 16)], 1u);
 }
 
 // statistics of the image in front of slot L (0 or 1) over rows [y0, y1)
@@ -196,11 +211,7 @@ __device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (mean) local += luma_of(q[k]);
-                else {
-                    atomicAdd(&hist[q[k] & 255u], 1u);
-                    atomicAdd(&hist[256u + ((q[k] >> 8) & 255u)], 1u);
-                    atomicAdd(&hist[512u + (q[k] >> 16)], 1u);
-                }
+                else hist_add(hist, q[k]);
             }
         }
     } else {
@@ -210,11 +221,7 @@ __device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_
             uint32_t r = dw.div(i);
             uint32_t p = Level<L>::at(c, (int)(i - r * c.W), y0 + (int)r);
             if (mean) local += luma_of(p);
-            else {
-                atomicAdd(&hist[p & 255u], 1u);
-                atomicAdd(&hist[256u + ((p >> 8) & 255u)], 1u);
-                atomicAdd(&hist[512u + (p >> 16)], 1u);
-            }
+            else hist_add(hist, p);
         }
     }
     if (mean) {
@@ -263,39 +270,39 @@ __device__ void build_slot_lut(int bands, uint32_t n_pixels, ImgState& st, int j
     __syncthreads();
 }
 
-// everything before the final pass for one source image; returns true when the cluster
-// exchanged statistics (=> peers may still be reading this CTA's shared memory)
-__device__ bool prepare_image(const AugParams& P, const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo,
-                              uint32_t s_len, int band, ImgState& st, cg::cluster_group& cluster) {
+__device__ __forceinline__ void zero_stats(ImgState& st) {
+    for (int i = threadIdx.x; i < 2 * 768; i += blockDim.x) (&st.hist[0][0])[i] = 0u;
+    if (threadIdx.x < 2) st.suml[threadIdx.x] = 0ull;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void compose_lut(ImgState& st, uint32_t lut_mask) {
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        uint32_t v = (uint32_t)(i & 255), base = (uint32_t)(i & ~255);
+        if (lut_mask & 1u) v = st.lut[0][base + v];
+        if (lut_mask & 2u) v = st.lut[1][base + v];
+        st.lutc[i] = (uint8_t)v;
+    }
+    __syncthreads();
+}
+
+// everything before the final pass for one (non-MAT) source image; returns true when the
+// cluster exchanged statistics (=> peers may still be reading this CTA's shared memory)
+__device__ bool prepare_image(const AugParams& P, const Ctx& c, int y0, int y1, ImgState& st, cg::cluster_group& cluster) {
     const uint32_t stat_mask = st.prog.stat_mask, lut_mask = st.prog.lut_mask;
     if (lut_mask == 0) return false;
-    const int y0 = (int)(((long long)band * P.H) / P.bands);
-    const int y1 = (int)(((long long)(band + 1) * P.H) / P.bands);
-    if (stat_mask) {
-        for (int i = threadIdx.x; i < 2 * 768; i += blockDim.x) (&st.hist[0][0])[i] = 0u;
-        if (threadIdx.x < 2) st.suml[threadIdx.x] = 0ull;
-        __syncthreads();
-    }
+    if (stat_mask) zero_stats(st);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         if (!((lut_mask >> j) & 1u)) continue;
         if ((stat_mask >> j) & 1u) {
-            Ctx c = make_ctx(raw, sraw, s_lo, s_len, P.H, P.W, st, true);
             const int kind = st.prog.op[j].kind;
             if (j == 0) accumulate_stats<0>(c, kind, y0, y1, st.hist[0], &st.suml[0]);
             else        accumulate_stats<1>(c, kind, y0, y1, st.hist[1], &st.suml[1]);
         }
         build_slot_lut(P.bands, (uint32_t)P.H * (uint32_t)P.W, st, j, cluster);
     }
-    if (st.prog.cls == C_LUT) {           // one lookup per channel in the final pass
-        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-            uint32_t v = (uint32_t)(i & 255), base = (uint32_t)(i & ~255);
-            if (lut_mask & 1u) v = st.lut[0][base + v];
-            if (lut_mask & 2u) v = st.lut[1][base + v];
-            st.lutc[i] = (uint8_t)v;
-        }
-        __syncthreads();
-    }
+    if (st.prog.cls == C_LUT) compose_lut(st, lut_mask);
     return stat_mask != 0;
 }
 
@@ -323,7 +330,8 @@ __device__ __forceinline__ uint32_t zero_mask(const TailInfo& t, int ox0, int oy
     return m;
 }
 
-// aligned classes: the four source pixels of an output quad are 12 contiguous bytes
+// aligned classes: the four source pixels of an output quad are 12 contiguous bytes.
+// `slot` is the op slot a C_SHARP program's Sharpness sits in (0) / its pointwise follower (1).
 template <int CLS>
 __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, const TailInfo& t, int out_w, int ox0,
                                          int oy, uint32_t px[4]) {
@@ -331,14 +339,27 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
     const int ay = oy + t.crop_dy;
     uint32_t q[4] = {0u, 0u, 0u, 0u};
     if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
-        load12(c, (uint32_t)(ay * c.W + sx0) * 3u, q);
-        if (CLS == C_LUT) {
+        const uint32_t off = (uint32_t)(ay * c.W + sx0) * 3u;
+        if (CLS == C_SHARP) {
+            const uint32_t pitch = (uint32_t)c.W * 3u;
+            const bool rowb = ay == 0 || ay == c.H - 1;
+            const uint8_t* r0 = src_ptr(c, off);
+            const uint8_t* rm = rowb ? r0 : src_ptr(c, off - pitch);
+            const uint8_t* rp = rowb ? r0 : src_ptr(c, off + pitch);
+            sharp_quad(rm, r0, rp, sx0 > 0, sx0 + 4 < c.W, rowb, sx0 == 0, sx0 + 4 == c.W,
+                       bits_to_float(c.op[0].a[0]), c.op[0].a[1] != 0, q);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) q[k] = apply_lut(lutc, q[k]);
-        } else if (CLS == C_POINT) {
+            for (int k = 0; k < 4; ++k) q[k] = apply_pointwise(c, 1, q[k], sx0 + k, ay);
+        } else {
+            load12(c, off, q);
+            if (CLS == C_LUT) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+                for (int k = 0; k < 4; ++k) q[k] = apply_lut(lutc, q[k]);
+            } else if (CLS == C_POINT) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+            }
         }
     }
     if (t.flip) { px[0] = q[3]; px[1] = q[2]; px[2] = q[1]; px[3] = q[0]; }
@@ -417,36 +438,146 @@ __device__ __forceinline__ void emit_quad(const AugParams& P, const float* s_nor
         for (int ch = 0; ch < 3; ++ch) {
             float v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float a = normalise<TAB>(P, s_norm, ch, (px_in[k] >> (8 * ch)) & 255u);
-                v[k] = ((zmask >> k) & 1u) ? 0.0f : a;
+            for (int k = 0; k < 4; ++k) v[k] = normalise<TAB>(P, s_norm, ch, (px_in[k] >> (8 * ch)) & 255u);
+            if (zmask) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = ((zmask >> k) & 1u) ? 0.0f : v[k];
             }
             store_plane4<OUT>(o + ch * plane, v, vec, nvalid);
         }
     }
 }
 
+// output rows [oy0, oy1) of one image through the class-specialised evaluator
 template <int OUT, bool TAB, int CLS>
-__device__ __forceinline__ void final_pass(const AugParams& P, const float* s_norm, const ImgState& st,
-                                           const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo, uint32_t s_len,
-                                           void* out_img, int band) {
-    const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
-    const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
+__device__ __forceinline__ void final_rows(const AugParams& P, const float* s_norm, const Ctx& c, const uint8_t* lutc,
+                                           const TailInfo& t, void* out_img, int oy0, int oy1) {
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
     const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
     FastDiv dq; dq.init(qpr);
     const bool vec = (P.out_w & 3) == 0;
-    const TailInfo t = make_tail(P, st.prog);
-    const Ctx c = make_ctx(raw, sraw, s_lo, s_len, P.H, P.W, st, CLS == C_POINT || CLS == C_GENERIC);
+    // incremental (row, quad) walk: one division up front, adds afterwards
+    uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
+    const uint32_t dr = dq.div(blockDim.x), dx = blockDim.x - dr * qpr;
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
-        const uint32_t r = dq.div(q);
-        const int ox0 = (int)(q - r * qpr) * 4;
+        const int ox0 = (int)qx * 4;
         const int oy = oy0 + (int)r;
         uint32_t px[4];
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
-        else quad_vec<CLS>(c, st.lutc, t, P.out_w, ox0, oy, px);
+        else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
+        qx += dx; r += dr;
+        if (qx >= qpr) { qx -= qpr; ++r; }
     }
+}
+
+template <int OUT, bool TAB>
+__device__ __forceinline__ void final_rows_cls(int cls, const AugParams& P, const float* s_norm, const Ctx& c,
+                                               const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1) {
+    switch (cls) {
+    case C_PLAIN: final_rows<OUT, TAB, C_PLAIN>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    case C_LUT:   final_rows<OUT, TAB, C_LUT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    case C_SHARP: final_rows<OUT, TAB, C_SHARP>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    default:      final_rows<OUT, TAB, C_GENERIC>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    }
+}
+
+// C_MAT: op0's output is materialised chunk by chunk into `mat` (uint8 HWC rows), then op1 - a
+// Sharpness or a statistics op - runs on the chunk as a single-op program.  Never re-evaluates
+// op0 nine times (lazy Sharpness) and keeps shared memory bounded for any image size.
+__device__ void fill_chunk(const Ctx& c, uint8_t* mat, int r0, int r1) {
+    const int W = c.W;
+    if ((W & 3) == 0) {
+        const uint32_t qpr = (uint32_t)W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
+        FastDiv dq; dq.init(qpr);
+        for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+            const uint32_t r = dq.div(q);
+            const int x0 = (int)(q - r * qpr) * 4, y = r0 + (int)r;
+            uint32_t p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = Level<1>::at(c, x0 + k, y);
+            uint32_t* w = reinterpret_cast<uint32_t*>(mat + (r * (uint32_t)W + (uint32_t)x0) * 3u);
+            w[0] = p[0] | (p[1] << 24);
+            w[1] = (p[1] >> 8) | (p[2] << 16);
+            w[2] = (p[2] >> 16) | (p[3] << 8);
+        }
+    } else {
+        const uint32_t n = (uint32_t)(r1 - r0) * (uint32_t)W;
+        FastDiv dw; dw.init((uint32_t)W);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t r = dw.div(i);
+            const uint32_t p = Level<1>::at(c, (int)(i - r * W), r0 + (int)r);
+            uint8_t* o = mat + i * 3u;
+            o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
+        }
+    }
+}
+
+template <int OUT, bool TAB>
+__device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgState& st, const Ctx& c, uint8_t* mat,
+                                 void* out_img, int band, cg::cluster_group& cluster) {
+    const int H = P.H, W = P.W;
+    const uint32_t pitch = (uint32_t)W * 3u;
+    const int k1 = st.prog.op[1].kind;
+    const bool stat1 = kind_needs_hist(k1) || kind_needs_mean(k1);
+    const int halo = (k1 == K_SHARPNESS) ? 1 : 0;
+    const int rows_cap = P.mat_cap / (int)pitch;                 // >= 3
+    const int step = rows_cap - 2 * halo;
+    const int y0 = (int)(((uint32_t)band * (uint32_t)H) / (uint32_t)P.bands);
+    const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)H) / (uint32_t)P.bands);
+    bool exchanged = false;
+
+    // op0's own LUT (and statistics over the raw band) first
+    if (st.prog.stat_mask) zero_stats(st);
+    if (st.prog.lut_mask & 1u) {
+        if (st.prog.stat_mask & 1u) {
+            accumulate_stats<0>(c, st.prog.op[0].kind, y0, y1, st.hist[0], &st.suml[0]);
+            exchanged = true;
+        }
+        build_slot_lut(P.bands, (uint32_t)H * (uint32_t)W, st, 0, cluster);
+    }
+    // the op1-only program that runs on the materialised rows
+    Ctx c2;
+    c2.raw = nullptr; c2.sraw = mat; c2.H = H; c2.W = W;
+    c2.op[0] = st.prog.op[1]; c2.box[0] = st.prog.box[1];
+    c2.op[1].kind = K_NONE; c2.box[1] = st.prog.box[1];
+    c2.lut[0] = st.lut[1]; c2.lut[1] = st.lut[1];
+
+    if (stat1) {                                                  // pass A: statistics of op0's output
+        for (int r = y0; r < y1; r += rows_cap) {
+            const int re = min(r + rows_cap, y1);
+            fill_chunk(c, mat, r, re);
+            __syncthreads();
+            c2.s_lo = (uint32_t)r * pitch; c2.s_len2 = (uint32_t)(re - r) * pitch - 2u;
+            accumulate_stats<0>(c2, k1, r, re, st.hist[1], &st.suml[1]);
+            __syncthreads();
+        }
+        exchanged = true;
+        build_slot_lut(P.bands, (uint32_t)H * (uint32_t)W, st, 1, cluster);
+        if (st.prog.cls2 == C_LUT) {                              // op1-only program: one LUT
+            for (int i = threadIdx.x; i < 768; i += blockDim.x) st.lutc[i] = st.lut[1][i];
+            __syncthreads();
+        }
+    }
+    // pass B: output rows, chunk by chunk
+    const TailInfo t = make_tail(P, st.prog);
+    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    for (int o = oy0; o < oy1; o += step) {
+        const int oe = min(o + step, oy1);
+        int r0 = o + t.crop_dy - halo, r1 = oe + t.crop_dy + halo;          // source rows of this chunk
+        if (r0 < 0) r0 = 0;
+        if (r1 > H) r1 = H;
+        if (r1 > r0) {
+            fill_chunk(c, mat, r0, r1);
+            c2.s_lo = (uint32_t)r0 * pitch; c2.s_len2 = (uint32_t)(r1 - r0) * pitch - 2u;
+        } else { c2.s_lo = 0; c2.s_len2 = 0; }
+        __syncthreads();
+        final_rows_cls<OUT, TAB>(st.prog.cls2, P, s_norm, c2, st.lutc, t, out_img, o, oe);
+        __syncthreads();
+    }
+    return exchanged;
 }
 
 // two sources mixed in fp32 (fused Mixup): class dispatch per quad, both contexts live
@@ -454,8 +585,8 @@ template <int OUT, bool TAB>
 __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const ImgState* st, const Ctx& c0,
                                const Ctx& c1, void* out_img, int band) {
     using T = typename OutElem<OUT>::T;
-    const int oy0 = (int)(((long long)band * P.out_h) / P.bands);
-    const int oy1 = (int)(((long long)(band + 1) * P.out_h) / P.bands);
+    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
     const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
     FastDiv dq; dq.init(qpr);
@@ -470,9 +601,11 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
         uint32_t pa[4], pb[4];
         if (cls0 == C_GENERIC) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_LUT) quad_vec<C_LUT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
+        else if (cls0 == C_SHARP) quad_vec<C_SHARP>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         if (cls1 == C_GENERIC) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_LUT) quad_vec<C_LUT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
+        else if (cls1 == C_SHARP) quad_vec<C_SHARP>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         const uint32_t za = zero_mask(t0, ox0, oy), zb = zero_mask(t1, ox0, oy);
         const int nvalid = min(4, P.out_w - ox0);
@@ -495,27 +628,36 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
 // launch 2
 template <int OUT, int NSRC, bool TAB>
 __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
-    extern __shared__ __align__(128) uint8_t s_band[];          // NSRC staged row bands
+    extern __shared__ __align__(128) uint8_t s_dyn[];           // NSRC staged row bands [+ materialisation chunk]
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st[NSRC];
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar[NSRC];
+    __shared__ int s_img;
 
     const int band = blockIdx.x;
-    const int img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
-    int src_idx[NSRC];
-    src_idx[0] = P.first + img;
-    if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
-
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
     uint32_t s_lo = 0, s_len = 0;
     if (P.stage) band_range(band, P.bands, P.H, P.W, P.out_h, P.crop_pad, img_bytes, s_lo, s_len);
+    if (TAB)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
+
+    // Programmatic dependent launch: everything above overlaps the resolve kernel's tail; the
+    // schedule and the programs it writes are only read after this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (threadIdx.x == 0) s_img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
+    __syncthreads();
+    const int img = s_img;
+    int src_idx[NSRC];
+    src_idx[0] = P.first + img;
+    if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
 
     // 0. stage the raw row band(s): one TMA bulk copy each, in flight while the program loads
     if (threadIdx.x == 0 && s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s)
-            tma_stage(&s_bar[s], s_band + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
+            tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
     }
     // per-image programs -> shared memory (24 words each)
 #pragma unroll
@@ -523,35 +665,36 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_ker
         if (threadIdx.x < sizeof(Prog) / 4)
             reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
                 __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
-    if (TAB)
-        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     __syncthreads();
     if (s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
     }
 
-    const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
-    bool any_stats = prepare_image(P, raw0, s_band, s_lo, s_len, band, st[0], cluster);
-    const uint8_t* raw1 = raw0;
-    if constexpr (NSRC == 2) {
-        raw1 = P.in + (size_t)src_idx[1] * img_bytes;
-        any_stats |= prepare_image(P, raw1, s_band + P.band_cap, s_lo, s_len, band, st[1], cluster);
-    }
-
+    const int y0 = (int)(((uint32_t)band * (uint32_t)P.H) / (uint32_t)P.bands);
+    const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.H) / (uint32_t)P.bands);
+    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
+    const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
+    bool any_stats = false;
 
     if constexpr (NSRC == 1) {
-        switch (st[0].prog.cls) {
-        case C_PLAIN: final_pass<OUT, TAB, C_PLAIN>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
-        case C_LUT:   final_pass<OUT, TAB, C_LUT>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
-        case C_POINT: final_pass<OUT, TAB, C_POINT>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
-        default:      final_pass<OUT, TAB, C_GENERIC>(P, s_norm, st[0], raw0, s_band, s_lo, s_len, out_img, band); break;
+        const int cls = st[0].prog.cls;
+        const Ctx c = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], cls != C_PLAIN && cls != C_LUT);
+        if (cls == C_MAT) {
+            any_stats = run_materialised<OUT, TAB>(P, s_norm, st[0], c, s_dyn + P.band_cap, out_img, band, cluster);
+        } else {
+            any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
+            final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
         }
     } else {
-        const Ctx c0 = make_ctx(raw0, s_band, s_lo, s_len, P.H, P.W, st[0], true);
-        const Ctx c1 = make_ctx(raw1, s_band + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
+        const uint8_t* raw1 = P.in + (size_t)src_idx[1] * img_bytes;
+        const Ctx c0 = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], true);
+        const Ctx c1 = make_ctx(raw1, s_dyn + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
+        any_stats = prepare_image(P, c0, y0, y1, st[0], cluster);
+        any_stats |= prepare_image(P, c1, y0, y1, st[1], cluster);
         final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
     }
 
@@ -596,7 +739,7 @@ uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
 
 template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
-    const size_t dyn = p.stage ? (size_t)p.band_cap * NSRC : 0;
+    const size_t dyn = (size_t)p.band_cap * NSRC + (size_t)p.mat_cap;
     static size_t configured = 0;                   // per instantiation
     if (dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB>,
@@ -609,13 +752,15 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)p.bands;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // overlap with the resolve kernel
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
 

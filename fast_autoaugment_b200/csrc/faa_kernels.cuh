@@ -21,6 +21,7 @@ struct ResolveParams {
     RngCfg rng;
     int32_t first, n;           // images [first, first+n) of the arrays above
     int32_t H, W, out_h, out_w, n_sub, n_op, op_base, apply_tail;
+    int32_t allow_mat;          // the pixel kernel has a materialisation chunk (single-source launches)
 };
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 
@@ -39,6 +40,8 @@ struct AugParams {
     int32_t stage;              // 1: TMA-stage the raw row band into shared memory
     int32_t band_cap;           // bytes of dynamic shared memory per staged band
     int32_t crop_pad;           // max |crop_dy| (RandomCrop padding)
+    int32_t mat_cap;            // bytes of the materialisation chunk (0: none), a whole number of rows >= 3
+    int32_t pdl;                // launched with programmatic stream serialization
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };

@@ -107,14 +107,22 @@ void quad_vec(int cls, const Ctx& c, const uint8_t* lutc, const TailInfo& t, int
     uint32_t q[4] = {0, 0, 0, 0};
     if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
         const uint8_t* b = c.raw + (uint32_t)(ay * c.W + sx0) * 3u;
-        uint32_t w[3]; memcpy(w, b, 12);
-        q[0] = w[0] & 0xFFFFFFu;
-        q[1] = (w[0] >> 24) | ((w[1] & 0xFFFFu) << 8);
-        q[2] = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
-        q[3] = w[2] >> 8;
-        for (int k = 0; k < 4; ++k) {
-            if (cls == C_LUT) q[k] = apply_lut(lutc, q[k]);
-            else if (cls == C_POINT) q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+        if (cls == C_SHARP) {
+            const uint32_t pitch = (uint32_t)c.W * 3u;
+            const bool rowb = ay == 0 || ay == c.H - 1;
+            sharp_quad(rowb ? b : b - pitch, b, rowb ? b : b + pitch, sx0 > 0, sx0 + 4 < c.W, rowb, sx0 == 0,
+                       sx0 + 4 == c.W, bits_to_float(c.op[0].a[0]), c.op[0].a[1] != 0, q);
+            for (int k = 0; k < 4; ++k) q[k] = apply_pointwise(c, 1, q[k], sx0 + k, ay);
+        } else {
+            uint32_t w[3]; memcpy(w, b, 12);
+            q[0] = w[0] & 0xFFFFFFu;
+            q[1] = (w[0] >> 24) | ((w[1] & 0xFFFFu) << 8);
+            q[2] = (w[1] >> 16) | ((w[2] & 0xFFu) << 16);
+            q[3] = w[2] >> 8;
+            for (int k = 0; k < 4; ++k) {
+                if (cls == C_LUT) q[k] = apply_lut(lutc, q[k]);
+                else if (cls == C_POINT) q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+            }
         }
     }
     for (int k = 0; k < 4; ++k) px[k] = t.flip ? q[3 - k] : q[k];
@@ -147,19 +155,51 @@ int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W
     const Box* boxes = (const Box*)boxes_v;
     const int nsrc = partner ? 2 : 1;
     std::vector<State> st(2);
+    std::vector<std::vector<uint8_t>> l1(2);
     const size_t img_bytes = (size_t)H * W * 3;
     const bool zb = use_zero_box && apply_tail;
     for (int img = 0; img < B; ++img) {
         int src[2] = {first + img, partner ? partner[img] : 0};
         Ctx c[2]; TailInfo t[2]; int cls[2];
         for (int k = 0; k < nsrc; ++k) {
+            // force_generic: no materialisation / vector classes (the kernel's mixup launches and fallbacks)
             build_prog(samples[src[k]], boxes + (size_t)src[k] * n_op, ops, n_op, op_base, apply_tail, H, W, out_w,
-                       st[k].prog);
+                       (force_generic || partner) ? 0 : 1, st[k].prog);
             if (force_generic) st[k].prog.cls = C_GENERIC;
-            prepare(in + img_bytes * src[k], H, W, st[k]);
-            c[k] = make_ctx(in + img_bytes * src[k], H, W, st[k]);
+            const uint8_t* raw = in + img_bytes * src[k];
             t[k] = make_tail(st[k].prog, zb);
-            cls[k] = st[k].prog.cls;
+            if (st[k].prog.cls == C_MAT) {
+                // like run_materialised(): op0's LUT, op0's output as an image, op1 as a single-op program on it
+                State& S = st[k];
+                memset(S.hist, 0, sizeof S.hist); S.suml[0] = S.suml[1] = 0;
+                Ctx c0 = make_ctx(raw, H, W, S);
+                if (S.prog.lut_mask & 1u) {
+                    if (S.prog.stat_mask & 1u) accumulate<0>(c0, S.prog.op[0].kind, S.hist[0], &S.suml[0]);
+                    build_lut(S, 0, H, W);
+                }
+                l1[k].resize(img_bytes);
+                for (int y = 0; y < H; ++y)
+                    for (int x = 0; x < W; ++x) {
+                        uint32_t p = Level<1>::at(c0, x, y);
+                        uint8_t* o = &l1[k][((size_t)y * W + x) * 3];
+                        o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
+                    }
+                Ctx c2 = make_ctx(l1[k].data(), H, W, S);
+                c2.op[0] = S.prog.op[1]; c2.box[0] = S.prog.box[1]; c2.op[1].kind = K_NONE;
+                c2.lut[0] = S.lut[1]; c2.lut[1] = S.lut[1];
+                const int k1 = S.prog.op[1].kind;
+                if (kind_needs_hist(k1) || kind_needs_mean(k1)) {
+                    accumulate<0>(c2, k1, S.hist[1], &S.suml[1]);
+                    build_lut(S, 1, H, W);
+                    memcpy(S.lutc, S.lut[1], 768);
+                }
+                c[k] = c2;
+                cls[k] = S.prog.cls2;
+            } else {
+                prepare(raw, H, W, st[k]);
+                c[k] = make_ctx(raw, H, W, st[k]);
+                cls[k] = st[k].prog.cls;
+            }
         }
         for (int oy = 0; oy < out_h; ++oy)
             for (int ox0 = 0; ox0 < out_w; ox0 += 4) {
@@ -199,7 +239,7 @@ int faa_emu_classes(const void* ops_v, int n_op, const void* samples_v, const vo
     const Box* boxes = (const Box*)boxes_v;
     for (int i = 0; i < B; ++i) {
         Prog g;
-        build_prog(samples[i], boxes + (size_t)i * n_op, ops, n_op, 0, apply_tail, H, W, out_w, g);
+        build_prog(samples[i], boxes + (size_t)i * n_op, ops, n_op, 0, apply_tail, H, W, out_w, 1, g);
         cls_out[i] = g.cls;
     }
     return 0;
