@@ -575,7 +575,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         const int pitch = w * 3;
         int rows = 16384 / pitch;
         if (rows > h + 2) rows = h + 2;
-        P.mat_cap = (!mat_off && !d_partner && rows >= 3) ? ((rows * pitch + 15) & ~15) : 0;
+        P.mat_cap = (!mat_off && !d_partner && rows >= 3) ? ((rows * pitch + 32 + 15) & ~15) : 0;   // + 2 guard bands
     }
     P.pdl = pdl_off ? 0 : 1;
     // launch 1: decisions -> programs (the whole pool when partners may be anywhere in it)

@@ -483,6 +483,10 @@ __device__ __forceinline__ void final_rows_cls(int cls, const AugParams& P, cons
     }
 }
 
+// (the chunk has a 16-byte guard band on both sides so that the vector paths' "is the 16-byte
+//  neighbourhood resident" tests succeed for its first and last pixels; guards are never used)
+constexpr uint32_t kMatGuard = 16;
+
 // C_MAT: op0's output is materialised chunk by chunk into `mat` (uint8 HWC rows), then op1 - a
 // Sharpness or a statistics op - runs on the chunk as a single-op program.  Never re-evaluates
 // op0 nine times (lazy Sharpness) and keeps shared memory bounded for any image size.
@@ -497,7 +501,7 @@ __device__ void fill_chunk(const Ctx& c, uint8_t* mat, int r0, int r1) {
             uint32_t p[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) p[k] = Level<1>::at(c, x0 + k, y);
-            uint32_t* w = reinterpret_cast<uint32_t*>(mat + (r * (uint32_t)W + (uint32_t)x0) * 3u);
+            uint32_t* w = reinterpret_cast<uint32_t*>(mat + kMatGuard + (r * (uint32_t)W + (uint32_t)x0) * 3u);
             w[0] = p[0] | (p[1] << 24);
             w[1] = (p[1] >> 8) | (p[2] << 16);
             w[2] = (p[2] >> 16) | (p[3] << 8);
@@ -508,7 +512,7 @@ __device__ void fill_chunk(const Ctx& c, uint8_t* mat, int r0, int r1) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t r = dw.div(i);
             const uint32_t p = Level<1>::at(c, (int)(i - r * W), r0 + (int)r);
-            uint8_t* o = mat + i * 3u;
+            uint8_t* o = mat + kMatGuard + i * 3u;
             o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
         }
     }
@@ -522,7 +526,7 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
     const int k1 = st.prog.op[1].kind;
     const bool stat1 = kind_needs_hist(k1) || kind_needs_mean(k1);
     const int halo = (k1 == K_SHARPNESS) ? 1 : 0;
-    const int rows_cap = P.mat_cap / (int)pitch;                 // >= 3
+    const int rows_cap = (P.mat_cap - 2 * (int)kMatGuard) / (int)pitch;      // >= 3
     const int step = rows_cap - 2 * halo;
     const int y0 = (int)(((uint32_t)band * (uint32_t)H) / (uint32_t)P.bands);
     const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)H) / (uint32_t)P.bands);
@@ -549,7 +553,7 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
             const int re = min(r + rows_cap, y1);
             fill_chunk(c, mat, r, re);
             __syncthreads();
-            c2.s_lo = (uint32_t)r * pitch; c2.s_len2 = (uint32_t)(re - r) * pitch - 2u;
+            c2.s_lo = (uint32_t)r * pitch - kMatGuard; c2.s_len2 = (uint32_t)(re - r) * pitch + 2u * kMatGuard - 2u;
             accumulate_stats<0>(c2, k1, r, re, st.hist[1], &st.suml[1]);
             __syncthreads();
         }
@@ -571,7 +575,7 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
         if (r1 > H) r1 = H;
         if (r1 > r0) {
             fill_chunk(c, mat, r0, r1);
-            c2.s_lo = (uint32_t)r0 * pitch; c2.s_len2 = (uint32_t)(r1 - r0) * pitch - 2u;
+            c2.s_lo = (uint32_t)r0 * pitch - kMatGuard; c2.s_len2 = (uint32_t)(r1 - r0) * pitch + 2u * kMatGuard - 2u;
         } else { c2.s_lo = 0; c2.s_len2 = 0; }
         __syncthreads();
         final_rows_cls<OUT, TAB>(st.prog.cls2, P, s_norm, c2, st.lutc, t, out_img, o, oe);
