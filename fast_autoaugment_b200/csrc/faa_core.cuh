@@ -424,10 +424,12 @@ FAA_HD void sharp_quad(const uint8_t* rm, const uint8_t* r0, const uint8_t* rp, 
     row6(rm, has_l, has_r, a);
     row6(rp, has_l, has_r, b);
     uint32_t rb[6], g[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         rb[i] = (a[i] & 0xFF00FFu) + (c[i] & 0xFF00FFu) + (b[i] & 0xFF00FFu);
         g[i] = ((a[i] >> 8) & 0xFFu) + ((c[i] >> 8) & 0xFFu) + ((b[i] >> 8) & 0xFFu);
     }
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t ctr = c[k + 1];
         if ((k == 0 && left_is_border) || (k == 3 && right_is_border)) { out[k] = ctr; continue; }
@@ -449,6 +451,7 @@ enum ProgClass : uint8_t {
     C_POINT = 2,     // pointwise incl. Color / Cutout, aligned
     C_GENERIC = 3,   // geometric ops, unaligned rows, ...: per-pixel lazy evaluation of the chain
     C_SHARP = 4,     // Sharpness on the raw image then a pointwise op, aligned: vectorised 3x3
+    C_GEOM = 6,      // one geometric op + pointwise ops: incremental fixed-point source coordinates
     C_MAT = 5        // op0 then (Sharpness | statistics op): op0's output is materialised chunk-wise in
                      // shared memory and op1 runs on it as a single-op program of class `cls2`
 };
@@ -510,7 +513,9 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
     if (allow_mat && k0 != K_NONE && (k1 == K_SHARPNESS || k1_stat)) {
         g.cls = C_MAT;
         g.cls2 = !aligned ? C_GENERIC : (k1 == K_SHARPNESS ? C_SHARP : C_LUT);
-    } else if (!aligned) g.cls = C_GENERIC;
+    } else if (((k0 == K_AFFINE || k0 == K_SHIFT) && kind_is_pointwise(k1)) ||
+               ((k1 == K_AFFINE || k1 == K_SHIFT) && kind_is_pointwise(k0))) g.cls = C_GEOM;
+    else if (!aligned) g.cls = C_GENERIC;
     else if (all_point) g.cls = n == 0 ? C_PLAIN : all_lut ? C_LUT : C_POINT;
     else if (k0 == K_SHARPNESS && kind_is_pointwise(k1)) g.cls = C_SHARP;
     else g.cls = C_GENERIC;

@@ -40,6 +40,9 @@ namespace cg = cooperative_groups;
 namespace faa {
 
 constexpr int kThreads = 256;
+#ifndef FAA_MIN_CTAS
+#define FAA_MIN_CTAS 4
+#endif
 constexpr int kCostBuckets = 8;
 
 struct __align__(16) ImgState {
@@ -136,8 +139,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 // the byte range of image rows a CTA may touch through the band-local paths
 __host__ __device__ inline void band_range(int band, int bands, int H, int W, int out_h, int crop_pad,
                                             uint32_t img_bytes, uint32_t& lo, uint32_t& len) {
-    const int y0 = (int)(((long long)band * H) / bands), y1 = (int)(((long long)(band + 1) * H) / bands);
-    const int oy0 = (int)(((long long)band * out_h) / bands), oy1 = (int)(((long long)(band + 1) * out_h) / bands);
+    const int y0 = (int)((uint32_t)(band * H) / (uint32_t)bands), y1 = (int)((uint32_t)((band + 1) * H) / (uint32_t)bands);
+    const int oy0 = (int)((uint32_t)(band * out_h) / (uint32_t)bands), oy1 = (int)((uint32_t)((band + 1) * out_h) / (uint32_t)bands);
     int r0 = (y0 < oy0 - crop_pad ? y0 : oy0 - crop_pad) - 1;
     int r1 = (y1 > oy1 + crop_pad ? y1 : oy1 + crop_pad) + 1;
     if (r0 < 0) r0 = 0;
@@ -239,13 +242,21 @@ __device__ void build_slot_lut(int bands, uint32_t n_pixels, ImgState& st, int j
     if (stats) {
         if (bands > 1) cluster.sync(); else __syncthreads();     // partials complete everywhere
         if (kind_needs_hist(kind)) {
-            for (int i = threadIdx.x; i < 768; i += blockDim.x) {
-                uint32_t t = 0;
-                for (int r = 0; r < bands; ++r) {
-                    const uint32_t* rem = (bands > 1) ? cluster.map_shared_rank(&st.hist[j][0], r) : &st.hist[j][0];
-                    t += rem[i];
+            if (bands > 1) {
+                // reduce-scatter over distributed shared memory: this CTA sums its slice of the 768
+                // bins over all ranks and writes the totals into every rank's `tot`
+                const int rank = (int)cluster.block_rank();
+                const int slice = (768 + bands - 1) / bands;
+                for (int i = threadIdx.x; i < slice; i += blockDim.x) {
+                    const int bin = rank * slice + i;
+                    if (bin < 768) {
+                        uint32_t t = 0;
+                        for (int r = 0; r < bands; ++r) t += cluster.map_shared_rank(&st.hist[j][0], r)[bin];
+                        for (int r = 0; r < bands; ++r) cluster.map_shared_rank(&st.tot[0], r)[bin] = t;
+                    }
                 }
-                st.tot[i] = t;
+            } else {
+                for (int i = threadIdx.x; i < 768; i += blockDim.x) st.tot[i] = st.hist[j][i];
             }
         } else {
             unsigned long long t = 0;
@@ -255,7 +266,8 @@ __device__ void build_slot_lut(int bands, uint32_t n_pixels, ImgState& st, int j
             }
             mean = contrast_mean(t, n_pixels);
         }
-        __syncthreads();
+        // totals visible everywhere; after this barrier no CTA touches a peer's shared memory
+        if (bands > 1) cluster.sync(); else __syncthreads();
     }
     if (kind_needs_hist(kind)) {
         const int t = threadIdx.x;
@@ -366,6 +378,41 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
     else { px[0] = q[0]; px[1] = q[1]; px[2] = q[2]; px[3] = q[3]; }
 }
 
+// C_GEOM: exactly one geometric op (slot g) and otherwise pointwise ops: the fixed-point source
+// coordinate is stepped along the quad instead of being re-derived per pixel
+__device__ __forceinline__ void quad_geom(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
+    const int g = (c.op[0].kind == K_AFFINE || c.op[0].kind == K_SHIFT) ? 0 : 1;
+    const OpRec& o = c.op[g];
+    const int ay = oy + t.crop_dy;
+    const int ax0 = (t.flip ? (out_w - 1 - ox0) : ox0) + t.crop_dx;
+    const int sx = t.flip ? -1 : 1;
+    const bool row_ok = (unsigned)ay < (unsigned)c.H;
+    int fx, fy, dfx, dfy;                              // 16.16 source coordinates of pixel k = 0 and their step
+    if (o.kind == K_AFFINE) {
+        fx = o.a[2] + o.a[0] * ax0 + o.a[1] * ay; fy = o.a[5] + o.a[3] * ax0 + o.a[4] * ay;
+        dfx = sx * o.a[0]; dfy = sx * o.a[3];
+    } else { fx = fy = dfx = dfy = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ax = ax0 + sx * k;
+        uint32_t p = 0u;
+        bool have = false;
+        int xs = 0, ys = 0;
+        if (row_ok && (unsigned)ax < (unsigned)c.W && ox0 + k < out_w) {
+            have = true;                                // (ax, ay) is a pixel of the augmented image
+            if (o.kind == K_AFFINE) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
+            else { xs = ax + o.a[0] + (ax >= o.a[2]); ys = ay + o.a[1] + (ay >= o.a[3]); }
+            const bool inside = (unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H;
+            if (inside) {
+                p = load_raw(c, xs, ys);
+                if (g == 1) p = apply_pointwise(c, 0, p, xs, ys);        // op0 ran before the gather
+            }
+            if (g == 0) p = apply_pointwise(c, 1, p, ax, ay);            // op1 runs after it (fill included)
+        }
+        px[k] = have ? p : 0u;
+    }
+}
+
 __device__ __forceinline__ void quad_generic(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
     const int ay = oy + t.crop_dy;
 #pragma unroll
@@ -464,6 +511,7 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
         const int oy = oy0 + (int)r;
         uint32_t px[4];
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_GEOM) quad_geom(c, t, P.out_w, ox0, oy, px);
         else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
         qx += dx; r += dr;
@@ -479,6 +527,7 @@ __device__ __forceinline__ void final_rows_cls(int cls, const AugParams& P, cons
     case C_LUT:   final_rows<OUT, TAB, C_LUT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     case C_SHARP: final_rows<OUT, TAB, C_SHARP>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    case C_GEOM:  final_rows<OUT, TAB, C_GEOM>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     default:      final_rows<OUT, TAB, C_GENERIC>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     }
 }
@@ -603,11 +652,11 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
         const int ox0 = (int)(q - r * qpr) * 4;
         const int oy = oy0 + (int)r;
         uint32_t pa[4], pb[4];
-        if (cls0 == C_GENERIC) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
+        if (cls0 == C_GENERIC || cls0 == C_GEOM) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_LUT) quad_vec<C_LUT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_SHARP) quad_vec<C_SHARP>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
-        if (cls1 == C_GENERIC) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
+        if (cls1 == C_GENERIC || cls1 == C_GEOM) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_LUT) quad_vec<C_LUT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_SHARP) quad_vec<C_SHARP>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
@@ -631,7 +680,7 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
 // ---------------------------------------------------------------------------------------
 // launch 2
 template <int OUT, int NSRC, bool TAB>
-__global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
+__global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
     extern __shared__ __align__(128) uint8_t s_dyn[];           // NSRC staged row bands [+ materialisation chunk]
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st[NSRC];
@@ -702,8 +751,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? 3 : 2)) faa_augment_ker
         final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
     }
 
-    // a CTA must not exit while cluster peers may still read its partial statistics
-    if (any_stats && P.bands > 1) cluster.sync();
+    (void)any_stats;   // statistics exchanges end with their own cluster barrier (build_slot_lut)
 }
 
 // out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math (aug_mixup.py:13-23)

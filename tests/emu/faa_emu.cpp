@@ -205,7 +205,7 @@ int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W
             for (int ox0 = 0; ox0 < out_w; ox0 += 4) {
                 uint32_t px[2][4], zm[2] = {0, 0};
                 for (int k = 0; k < nsrc; ++k) {
-                    if (cls[k] == C_GENERIC) quad_generic(c[k], t[k], out_w, ox0, oy, px[k]);
+                    if (cls[k] == C_GENERIC || cls[k] == C_GEOM) quad_generic(c[k], t[k], out_w, ox0, oy, px[k]);
                     else quad_vec(cls[k], c[k], st[k].lutc, t[k], out_w, ox0, oy, px[k]);
                     zm[k] = zero_mask(t[k], ox0, oy);
                 }
