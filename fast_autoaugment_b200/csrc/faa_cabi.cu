@@ -204,6 +204,8 @@ struct faa_policy {
     // scratch of faa_augment_host
     void* d_progs = nullptr; size_t d_progs_bytes = 0;
     void* d_order = nullptr;             // int32 [capacity of d_progs in images]
+    void* d_scratch = nullptr; size_t d_scratch_bytes = 0;   // Sharpness->gather scratch images
+    bool has_sg = false;                 // some sub-policy has Sharpness followed by a geometric op
     void* d_in = nullptr; size_t d_in_bytes = 0;
     void* d_out = nullptr; size_t d_out_bytes = 0;
     void* h_in_stage = nullptr; size_t h_in_bytes = 0;
@@ -272,6 +274,11 @@ int faa_policy_create(const int32_t* op_ids, const double* probs, const double* 
     p->op_ids.assign(op_ids, op_ids + n);
     p->probs.assign(probs, probs + n);
     p->levels.assign(levels, levels + n);
+    auto is_geo = [](int id) { return id == FAA_SHEAR_X || id == FAA_SHEAR_Y || id == FAA_TRANSLATE_X || id == FAA_TRANSLATE_Y ||
+                                      id == FAA_ROTATE || id == FAA_TRANSLATE_X_ABS || id == FAA_TRANSLATE_Y_ABS; };
+    for (int s = 0; s < n_sub && !p->has_sg; ++s)
+        for (int j = 0; j + 1 < n_op; ++j)
+            if (op_ids[(size_t)s * n_op + j] == FAA_SHARPNESS && is_geo(op_ids[(size_t)s * n_op + j + 1])) p->has_sg = true;
     *out = p;
     return FAA_OK;
 }
@@ -283,6 +290,7 @@ int faa_policy_destroy(faa_policy_t* p) {
     if (p->d_norm) cudaFree(p->d_norm);
     if (p->d_progs) cudaFree(p->d_progs);
     if (p->d_order) cudaFree(p->d_order);
+    if (p->d_scratch) cudaFree(p->d_scratch);
     if (p->d_in) cudaFree(p->d_in);
     if (p->d_out) cudaFree(p->d_out);
     if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
@@ -555,7 +563,8 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
     P.lam = lam; P.one_minus_lam = oml;
     P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
-    P.order = d_partner ? nullptr : reinterpret_cast<const int32_t*>(p->d_order);
+    static const bool lpt_off = [] { const char* e = getenv("FAA_LPT"); return e && e[0] == '0'; }();
+    P.order = (d_partner || lpt_off) ? nullptr : reinterpret_cast<const int32_t*>(p->d_order);
     // TMA band staging needs 16-byte aligned image bases and a band that fits shared memory
     // (crop_pad only sizes the staged band; rows outside it are read from global memory)
     P.crop_pad = tail->crop_pad > 0 ? tail->crop_pad : 0;
@@ -588,7 +597,17 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     R.first = d_partner ? 0 : first; R.n = d_partner ? n_all : batch;
     R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
     R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = op_base; R.apply_tail = apply_tail;
-    R.allow_mat = P.mat_cap > 0 ? 1 : 0;
+    R.allow = P.mat_cap > 0 ? 1 : 0;
+    if (p->has_sg && !d_partner && (w & 3) == 0) {       // scratch images for Sharpness->gather programs
+        const size_t need = (size_t)n_all * img_bytes;
+        if (p->d_scratch_bytes < need) {
+            if (p->d_scratch) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(p->d_scratch)); p->d_scratch = nullptr; p->d_scratch_bytes = 0; }
+            CK(cudaMalloc(&p->d_scratch, need));
+            p->d_scratch_bytes = need;
+        }
+        P.scratch = (uint8_t*)p->d_scratch;
+        R.allow |= 2;
+    }
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
     CK(launch_resolve(R, stream));

@@ -452,6 +452,8 @@ enum ProgClass : uint8_t {
     C_GENERIC = 3,   // geometric ops, unaligned rows, ...: per-pixel lazy evaluation of the chain
     C_SHARP = 4,     // Sharpness on the raw image then a pointwise op, aligned: vectorised 3x3
     C_GEOM = 6,      // one geometric op + pointwise ops: incremental fixed-point source coordinates
+    C_SG = 7,        // Sharpness then a geometric op: the sharpened image goes through a global scratch
+                     // image (L2-resident), then the gather reads it - no 9-tap re-evaluation per gather
     C_MAT = 5        // op0 then (Sharpness | statistics op): op0's output is materialised chunk-wise in
                      // shared memory and op1 runs on it as a single-op program of class `cls2`
 };
@@ -470,9 +472,11 @@ struct Prog {        // 96 bytes
 FAA_HD bool kind_is_lutlike(int k) { return k == K_NONE || kind_uses_lut(k); }
 
 // Sample + boxes -> Prog.  ops: compiled table [n_sub][n_op][2]; boxes: this sample's n_op boxes.
-// allow_mat: the launch has a materialisation buffer of at least 3 rows (single-source launches).
+// allow: bit 0 = the launch has a materialisation chunk of at least 3 rows, bit 1 = it has a global
+// scratch image (both only for single-source launches).
 FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, int n_op, int op_base,
-                       int apply_tail, int H, int W, int out_w, int allow_mat, Prog& g) {
+                       int apply_tail, int H, int W, int out_w, int allow, Prog& g) {
+    const bool allow_mat = (allow & 1) != 0, allow_scratch = (allow & 2) != 0;
     Sample s = s_in;
     if (!apply_tail) { s.crop_dx = s.crop_dy = 0; s.flip = 0; s.zero_box[0] = s.zero_box[1] = s.zero_box[2] = s.zero_box[3] = 0; }
     g.crop_dy = s.crop_dy; g.crop_dx = s.crop_dx; g.flip = s.flip;
@@ -510,9 +514,14 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
     const int k0 = g.op[0].kind, k1 = g.op[1].kind;
     const bool aligned = ((W & 3) == 0) && ((out_w & 3) == 0) && ((s.crop_dx & 3) == 0);
     const bool k1_stat = kind_needs_hist(k1) || kind_needs_mean(k1);
-    if (allow_mat && k0 != K_NONE && (k1 == K_SHARPNESS || k1_stat)) {
+    // a histogram op behind per-channel LUT ops needs no second pass: its histogram is the raw
+    // histogram pushed forward through the first LUT
+    const bool push = k0 != K_NONE && kind_is_lutlike(k0) && kind_needs_hist(k1);
+    if (allow_mat && k0 != K_NONE && (k1 == K_SHARPNESS || (k1_stat && !push))) {
         g.cls = C_MAT;
         g.cls2 = !aligned ? C_GENERIC : (k1 == K_SHARPNESS ? C_SHARP : C_LUT);
+    } else if (allow_scratch && k0 == K_SHARPNESS && (k1 == K_AFFINE || k1 == K_SHIFT) && (W & 3) == 0) {
+        g.cls = C_SG;
     } else if (((k0 == K_AFFINE || k0 == K_SHIFT) && kind_is_pointwise(k1)) ||
                ((k1 == K_AFFINE || k1 == K_SHIFT) && kind_is_pointwise(k0))) g.cls = C_GEOM;
     else if (!aligned) g.cls = C_GENERIC;
@@ -529,9 +538,10 @@ FAA_HD uint32_t op_unit_cost(int k) {
 FAA_HD uint32_t prog_cost(const Prog& g) {
     const int k0 = g.op[0].kind, k1 = g.op[1].kind;
     uint32_t c0 = op_unit_cost(k0), c1 = op_unit_cost(k1);
-    if (g.cls == C_SHARP) c0 = 5u;
+    if (g.cls == C_SHARP || g.cls == C_SG) c0 = 5u;
     if (g.cls == C_MAT && g.cls2 == C_SHARP) c1 = 5u;
     uint32_t chain = (k1 == K_SHARPNESS && g.cls != C_MAT) ? c1 + 9u * c0 : c0 + c1;   // lazy Sharpness: 9 taps below it
+    if (k0 == K_SHARPNESS && (k1 == K_AFFINE || k1 == K_SHIFT) && g.cls != C_SG) chain = c1 + 9u * 4u;
     uint32_t cost = 2u + chain + (g.cls == C_GENERIC ? 2u : 0u);
     if (g.stat_mask & 1u) cost += 2u;                                    // extra pass over the raw band
     if (g.stat_mask & 2u) cost += 2u + c0;                               // extra pass evaluating op 0

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
         }
         if (P.progs != nullptr) {
             Prog g;
-            build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, P.allow_mat, g);
+            build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, P.allow, g);
             g.bucket = (uint8_t)cost_bucket(prog_cost(g));
             P.progs[i] = g;
             atomicAdd(&s_count[g.bucket], 1);
@@ -177,7 +177,7 @@ __device__ __forceinline__ void unpack12(uint32_t w0, uint32_t w1, uint32_t w2, 
 __device__ __forceinline__ const uint8_t* src_ptr(const Ctx& c, uint32_t off) {
     const uint32_t rel = off - c.s_lo;
     const uint32_t lim = c.s_len2 > 18u ? c.s_len2 - 14u : 0u;          // rel >= 4 and rel + 16 <= staged length
-    return (rel - 4u < lim - 4u) ? c.sraw + rel : c.raw + off;
+    return (lim >= 4u && rel - 4u < lim - 4u) ? c.sraw + rel : c.raw + off;
 }
 
 // 12 contiguous, 4-byte aligned bytes of the raw image at byte offset `off`
@@ -199,10 +199,11 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t p) {
     atomicAdd(&hist[512u + (p >> 16)], 1u);
 }
 
-// statistics of the image in front of slot L (0 or 1) over rows [y0, y1)
+// statistics of the image in front of slot L (0 or 1) over rows [y0, y1):
+// per-channel histogram and / or the luma sum
 template <int L>
-__device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_t* hist, unsigned long long* suml) {
-    const bool mean = kind == K_CONTRAST;
+__device__ void accumulate_stats(const Ctx& c, bool want_hist, bool want_mean, int y0, int y1, uint32_t* hist,
+                                 unsigned long long* suml) {
     uint32_t local = 0;
     if (L == 0 && (c.W & 3) == 0) {
         // raw image: 4 pixels per thread from 12 aligned bytes
@@ -213,8 +214,8 @@ __device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_
             load12(c, base + 12u * i, q);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (mean) local += luma_of(q[k]);
-                else hist_add(hist, q[k]);
+                if (want_mean) local += luma_of(q[k]);
+                if (want_hist) hist_add(hist, q[k]);
             }
         }
     } else {
@@ -223,52 +224,56 @@ __device__ void accumulate_stats(const Ctx& c, int kind, int y0, int y1, uint32_
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             uint32_t r = dw.div(i);
             uint32_t p = Level<L>::at(c, (int)(i - r * c.W), y0 + (int)r);
-            if (mean) local += luma_of(p);
-            else hist_add(hist, p);
+            if (want_mean) local += luma_of(p);
+            if (want_hist) hist_add(hist, p);
         }
     }
-    if (mean) {
+    if (want_mean) {
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if ((threadIdx.x & 31) == 0) atomicAdd(suml, (unsigned long long)local);
     }
 }
 
-// reduce slot j's partial statistics over the cluster and build its LUT
-__device__ void build_slot_lut(int bands, uint32_t n_pixels, ImgState& st, int j, cg::cluster_group& cluster) {
-    const OpRec o = st.prog.op[j];
-    const int kind = o.kind;
-    const bool stats = kind_needs_hist(kind) || kind_needs_mean(kind);
+// cluster-wide totals of slot j's partial statistics: histogram -> st.tot (every CTA), luma -> mean
+__device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool want_hist, bool want_mean, ImgState& st, int j,
+                                   cg::cluster_group& cluster) {
     uint32_t mean = 0;
-    if (stats) {
-        if (bands > 1) cluster.sync(); else __syncthreads();     // partials complete everywhere
-        if (kind_needs_hist(kind)) {
-            if (bands > 1) {
-                // reduce-scatter over distributed shared memory: this CTA sums its slice of the 768
-                // bins over all ranks and writes the totals into every rank's `tot`
-                const int rank = (int)cluster.block_rank();
-                const int slice = (768 + bands - 1) / bands;
-                for (int i = threadIdx.x; i < slice; i += blockDim.x) {
-                    const int bin = rank * slice + i;
-                    if (bin < 768) {
-                        uint32_t t = 0;
-                        for (int r = 0; r < bands; ++r) t += cluster.map_shared_rank(&st.hist[j][0], r)[bin];
-                        for (int r = 0; r < bands; ++r) cluster.map_shared_rank(&st.tot[0], r)[bin] = t;
-                    }
+    if (bands > 1) cluster.sync(); else __syncthreads();         // partials complete everywhere
+    if (want_hist) {
+        if (bands > 1) {
+            // reduce-scatter over distributed shared memory: this CTA sums its slice of the 768
+            // bins over all ranks and writes the totals into every rank's `tot`
+            const int rank = (int)cluster.block_rank();
+            const int slice = (768 + bands - 1) / bands;
+            for (int i = threadIdx.x; i < slice; i += blockDim.x) {
+                const int bin = rank * slice + i;
+                if (bin < 768) {
+                    uint32_t t = 0;
+                    for (int r = 0; r < bands; ++r) t += cluster.map_shared_rank(&st.hist[j][0], r)[bin];
+                    for (int r = 0; r < bands; ++r) cluster.map_shared_rank(&st.tot[0], r)[bin] = t;
                 }
-            } else {
-                for (int i = threadIdx.x; i < 768; i += blockDim.x) st.tot[i] = st.hist[j][i];
             }
         } else {
-            unsigned long long t = 0;
-            for (int r = 0; r < bands; ++r) {
-                const unsigned long long* rem = (bands > 1) ? cluster.map_shared_rank(&st.suml[j], r) : &st.suml[j];
-                t += *rem;
-            }
-            mean = contrast_mean(t, n_pixels);
+            for (int i = threadIdx.x; i < 768; i += blockDim.x) st.tot[i] = st.hist[j][i];
         }
-        // totals visible everywhere; after this barrier no CTA touches a peer's shared memory
-        if (bands > 1) cluster.sync(); else __syncthreads();
     }
+    if (want_mean) {
+        unsigned long long t = 0;
+        for (int r = 0; r < bands; ++r) {
+            const unsigned long long* rem = (bands > 1) ? cluster.map_shared_rank(&st.suml[j], r) : &st.suml[j];
+            t += *rem;
+        }
+        mean = contrast_mean(t, n_pixels);
+    }
+    // totals visible everywhere; after this barrier no CTA touches a peer's shared memory
+    if (bands > 1) cluster.sync(); else __syncthreads();
+    return mean;
+}
+
+// slot j's 3x256 LUT from st.tot (histogram ops) or from the op's parameters (+ mean)
+__device__ void make_lut(uint32_t n_pixels, ImgState& st, int j, uint32_t mean) {
+    const OpRec o = st.prog.op[j];
+    const int kind = o.kind;
     if (kind_needs_hist(kind)) {
         const int t = threadIdx.x;
         if (t < 96) st.parts[t >> 5][t & 31] = hist_part(&st.tot[(t >> 5) * 256], t & 31);
@@ -298,21 +303,38 @@ __device__ __forceinline__ void compose_lut(ImgState& st, uint32_t lut_mask) {
     __syncthreads();
 }
 
-// everything before the final pass for one (non-MAT) source image; returns true when the
-// cluster exchanged statistics (=> peers may still be reading this CTA's shared memory)
+// everything before the final pass for one (non-MAT) source image
 __device__ bool prepare_image(const AugParams& P, const Ctx& c, int y0, int y1, ImgState& st, cg::cluster_group& cluster) {
     const uint32_t stat_mask = st.prog.stat_mask, lut_mask = st.prog.lut_mask;
     if (lut_mask == 0) return false;
-    if (stat_mask) zero_stats(st);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        if (!((lut_mask >> j) & 1u)) continue;
-        if ((stat_mask >> j) & 1u) {
-            const int kind = st.prog.op[j].kind;
-            if (j == 0) accumulate_stats<0>(c, kind, y0, y1, st.hist[0], &st.suml[0]);
-            else        accumulate_stats<1>(c, kind, y0, y1, st.hist[1], &st.suml[1]);
+    const uint32_t n_pixels = (uint32_t)P.H * (uint32_t)P.W;
+    const int k0 = st.prog.op[0].kind, k1 = st.prog.op[1].kind;
+    // histogram op behind LUT ops: raw histogram pushed forward through the first LUT (no 2nd pass)
+    const bool push = k0 != K_NONE && kind_is_lutlike(k0) && kind_needs_hist(k1);
+    const bool hist0 = kind_needs_hist(k0) || push, mean0 = kind_needs_mean(k0);
+    if (stat_mask || push) zero_stats(st);
+    if (lut_mask & 1u) {
+        uint32_t mean = 0;
+        if (hist0 || mean0) {
+            accumulate_stats<0>(c, hist0, mean0, y0, y1, st.hist[0], &st.suml[0]);
+            mean = exchange_stats(P.bands, n_pixels, hist0, mean0, st, 0, cluster);
         }
-        build_slot_lut(P.bands, (uint32_t)P.H * (uint32_t)P.W, st, j, cluster);
+        make_lut(n_pixels, st, 0, mean);
+    }
+    if (lut_mask & 2u) {
+        uint32_t mean = 0;
+        if (push) {
+            // st.tot holds the cluster totals of the raw histogram; hist[1] is zero
+            for (int i = threadIdx.x; i < 768; i += blockDim.x)
+                atomicAdd(&st.hist[1][(i & ~255) + st.lut[0][i]], st.tot[i]);
+            __syncthreads();
+            for (int i = threadIdx.x; i < 768; i += blockDim.x) st.tot[i] = st.hist[1][i];
+            __syncthreads();
+        } else if ((stat_mask >> 1) & 1u) {      // lazy fallback (no materialisation chunk available)
+            accumulate_stats<1>(c, kind_needs_hist(k1), kind_needs_mean(k1), y0, y1, st.hist[1], &st.suml[1]);
+            mean = exchange_stats(P.bands, n_pixels, kind_needs_hist(k1), kind_needs_mean(k1), st, 1, cluster);
+        }
+        make_lut(n_pixels, st, 1, mean);
     }
     if (st.prog.cls == C_LUT) compose_lut(st, lut_mask);
     return stat_mask != 0;
@@ -380,6 +402,11 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
 
 // C_GEOM: exactly one geometric op (slot g) and otherwise pointwise ops: the fixed-point source
 // coordinate is stepped along the quad instead of being re-derived per pixel
+__device__ __forceinline__ uint32_t load_raw_cg(const Ctx& c, int x, int y) {     // scratch written by this kernel
+    const uint8_t* p = c.raw + (uint32_t)(y * c.W + x) * 3u;
+    return (uint32_t)__ldcg(p) | ((uint32_t)__ldcg(p + 1) << 8) | ((uint32_t)__ldcg(p + 2) << 16);
+}
+template <bool COH>
 __device__ __forceinline__ void quad_geom(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
     const int g = (c.op[0].kind == K_AFFINE || c.op[0].kind == K_SHIFT) ? 0 : 1;
     const OpRec& o = c.op[g];
@@ -404,7 +431,7 @@ __device__ __forceinline__ void quad_geom(const Ctx& c, const TailInfo& t, int o
             else { xs = ax + o.a[0] + (ax >= o.a[2]); ys = ay + o.a[1] + (ay >= o.a[3]); }
             const bool inside = (unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H;
             if (inside) {
-                p = load_raw(c, xs, ys);
+                p = COH ? load_raw_cg(c, xs, ys) : load_raw(c, xs, ys);
                 if (g == 1) p = apply_pointwise(c, 0, p, xs, ys);        // op0 ran before the gather
             }
             if (g == 0) p = apply_pointwise(c, 1, p, ax, ay);            // op1 runs after it (fill included)
@@ -511,7 +538,8 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
         const int oy = oy0 + (int)r;
         uint32_t px[4];
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
-        else if (CLS == C_GEOM) quad_geom(c, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_GEOM) quad_geom<false>(c, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_SG) quad_geom<true>(c, t, P.out_w, ox0, oy, px);
         else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
         qx += dx; r += dr;
@@ -528,6 +556,7 @@ __device__ __forceinline__ void final_rows_cls(int cls, const AugParams& P, cons
     case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     case C_SHARP: final_rows<OUT, TAB, C_SHARP>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     case C_GEOM:  final_rows<OUT, TAB, C_GEOM>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    case C_SG:    final_rows<OUT, TAB, C_SG>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     default:      final_rows<OUT, TAB, C_GENERIC>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     }
 }
@@ -539,18 +568,28 @@ constexpr uint32_t kMatGuard = 16;
 // C_MAT: op0's output is materialised chunk by chunk into `mat` (uint8 HWC rows), then op1 - a
 // Sharpness or a statistics op - runs on the chunk as a single-op program.  Never re-evaluates
 // op0 nine times (lazy Sharpness) and keeps shared memory bounded for any image size.
-__device__ void fill_chunk(const Ctx& c, uint8_t* mat, int r0, int r1) {
+// rows [r0, r1) of op0's output (op1 disabled in `c`) -> dst (+ row pitch), through the
+// class-specialised single-op evaluators (cls0) when the width allows 4-pixel quads
+__device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* dst, int r0, int r1) {
     const int W = c.W;
     if ((W & 3) == 0) {
         const uint32_t qpr = (uint32_t)W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
         FastDiv dq; dq.init(qpr);
+        TailInfo id; id.crop_dy = id.crop_dx = id.flip = 0; id.zb0 = id.zb1 = id.zb2 = id.zb3 = 0;
         for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
             const uint32_t r = dq.div(q);
             const int x0 = (int)(q - r * qpr) * 4, y = r0 + (int)r;
             uint32_t p[4];
+            switch (cls0) {
+            case C_LUT:   quad_vec<C_LUT>(c, lut0, id, W, x0, y, p); break;
+            case C_POINT: quad_vec<C_POINT>(c, lut0, id, W, x0, y, p); break;
+            case C_SHARP: quad_vec<C_SHARP>(c, lut0, id, W, x0, y, p); break;
+            case C_GEOM:  quad_geom<false>(c, id, W, x0, y, p); break;
+            default:
 #pragma unroll
-            for (int k = 0; k < 4; ++k) p[k] = Level<1>::at(c, x0 + k, y);
-            uint32_t* w = reinterpret_cast<uint32_t*>(mat + kMatGuard + (r * (uint32_t)W + (uint32_t)x0) * 3u);
+                for (int k = 0; k < 4; ++k) p[k] = Level<1>::at(c, x0 + k, y);
+            }
+            uint32_t* w = reinterpret_cast<uint32_t*>(dst + (r * (uint32_t)W + (uint32_t)x0) * 3u);
             w[0] = p[0] | (p[1] << 24);
             w[1] = (p[1] >> 8) | (p[2] << 16);
             w[2] = (p[2] >> 16) | (p[3] << 8);
@@ -561,10 +600,18 @@ __device__ void fill_chunk(const Ctx& c, uint8_t* mat, int r0, int r1) {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t r = dw.div(i);
             const uint32_t p = Level<1>::at(c, (int)(i - r * W), r0 + (int)r);
-            uint8_t* o = mat + kMatGuard + i * 3u;
+            uint8_t* o = dst + i * 3u;
             o[0] = (uint8_t)p; o[1] = (uint8_t)(p >> 8); o[2] = (uint8_t)(p >> 16);
         }
     }
+}
+
+__device__ __forceinline__ int single_op_class(int kind, int W) {
+    if (W & 3) return C_GENERIC;
+    if (kind == K_SHARPNESS) return C_SHARP;
+    if (kind == K_AFFINE || kind == K_SHIFT) return C_GEOM;
+    if (kind_uses_lut(kind)) return C_LUT;
+    return C_POINT;
 }
 
 template <int OUT, bool TAB>
@@ -582,14 +629,21 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
     bool exchanged = false;
 
     // op0's own LUT (and statistics over the raw band) first
+    const uint32_t n_pixels = (uint32_t)H * (uint32_t)W;
+    const int k0 = st.prog.op[0].kind;
     if (st.prog.stat_mask) zero_stats(st);
     if (st.prog.lut_mask & 1u) {
+        uint32_t mean = 0;
         if (st.prog.stat_mask & 1u) {
-            accumulate_stats<0>(c, st.prog.op[0].kind, y0, y1, st.hist[0], &st.suml[0]);
+            accumulate_stats<0>(c, kind_needs_hist(k0), kind_needs_mean(k0), y0, y1, st.hist[0], &st.suml[0]);
+            mean = exchange_stats(P.bands, n_pixels, kind_needs_hist(k0), kind_needs_mean(k0), st, 0, cluster);
             exchanged = true;
         }
-        build_slot_lut(P.bands, (uint32_t)H * (uint32_t)W, st, 0, cluster);
+        make_lut(n_pixels, st, 0, mean);
     }
+    Ctx c0 = c;                                                   // op0 alone, evaluated into the chunk
+    c0.op[1].kind = K_NONE;
+    const int cls0 = single_op_class(k0, W);
     // the op1-only program that runs on the materialised rows
     Ctx c2;
     c2.raw = nullptr; c2.sraw = mat; c2.H = H; c2.W = W;
@@ -600,14 +654,15 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
     if (stat1) {                                                  // pass A: statistics of op0's output
         for (int r = y0; r < y1; r += rows_cap) {
             const int re = min(r + rows_cap, y1);
-            fill_chunk(c, mat, r, re);
+            fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, r, re);
             __syncthreads();
             c2.s_lo = (uint32_t)r * pitch - kMatGuard; c2.s_len2 = (uint32_t)(re - r) * pitch + 2u * kMatGuard - 2u;
-            accumulate_stats<0>(c2, k1, r, re, st.hist[1], &st.suml[1]);
+            accumulate_stats<0>(c2, kind_needs_hist(k1), kind_needs_mean(k1), r, re, st.hist[1], &st.suml[1]);
             __syncthreads();
         }
         exchanged = true;
-        build_slot_lut(P.bands, (uint32_t)H * (uint32_t)W, st, 1, cluster);
+        const uint32_t mean1 = exchange_stats(P.bands, n_pixels, kind_needs_hist(k1), kind_needs_mean(k1), st, 1, cluster);
+        make_lut(n_pixels, st, 1, mean1);
         if (st.prog.cls2 == C_LUT) {                              // op1-only program: one LUT
             for (int i = threadIdx.x; i < 768; i += blockDim.x) st.lutc[i] = st.lut[1][i];
             __syncthreads();
@@ -623,7 +678,7 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
         if (r0 < 0) r0 = 0;
         if (r1 > H) r1 = H;
         if (r1 > r0) {
-            fill_chunk(c, mat, r0, r1);
+            fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, r0, r1);
             c2.s_lo = (uint32_t)r0 * pitch - kMatGuard; c2.s_len2 = (uint32_t)(r1 - r0) * pitch + 2u * kMatGuard - 2u;
         } else { c2.s_lo = 0; c2.s_len2 = 0; }
         __syncthreads();
@@ -652,11 +707,11 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
         const int ox0 = (int)(q - r * qpr) * 4;
         const int oy = oy0 + (int)r;
         uint32_t pa[4], pb[4];
-        if (cls0 == C_GENERIC || cls0 == C_GEOM) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
+        if (cls0 == C_GENERIC || cls0 == C_GEOM || cls0 == C_SG) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_LUT) quad_vec<C_LUT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_SHARP) quad_vec<C_SHARP>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
-        if (cls1 == C_GENERIC || cls1 == C_GEOM) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
+        if (cls1 == C_GENERIC || cls1 == C_GEOM || cls1 == C_SG) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_LUT) quad_vec<C_LUT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_SHARP) quad_vec<C_SHARP>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
@@ -738,6 +793,18 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
         const Ctx c = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], cls != C_PLAIN && cls != C_LUT);
         if (cls == C_MAT) {
             any_stats = run_materialised<OUT, TAB>(P, s_norm, st[0], c, s_dyn + P.band_cap, out_img, band, cluster);
+        } else if (cls == C_SG) {
+            // Sharpness then a gather: the band of the sharpened image goes to the global scratch
+            // image, the whole cluster synchronises, then the gather reads scratch (coherent loads)
+            uint8_t* scr = P.scratch + (size_t)src_idx[0] * img_bytes;
+            Ctx cs = c; cs.op[1].kind = K_NONE;
+            fill_rows(cs, C_SHARP, st[0].lut[0], scr + (uint32_t)y0 * (uint32_t)P.W * 3u, y0, y1);
+            __threadfence();
+            if (P.bands > 1) cluster.sync(); else __syncthreads();
+            Ctx cg2 = c;
+            cg2.raw = scr; cg2.s_len2 = 0;
+            cg2.op[0] = c.op[1]; cg2.box[0] = c.box[1]; cg2.op[1].kind = K_NONE;
+            final_rows_cls<OUT, TAB>(C_SG, P, s_norm, cg2, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
         } else {
             any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
             final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);

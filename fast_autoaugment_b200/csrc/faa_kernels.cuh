@@ -21,7 +21,7 @@ struct ResolveParams {
     RngCfg rng;
     int32_t first, n;           // images [first, first+n) of the arrays above
     int32_t H, W, out_h, out_w, n_sub, n_op, op_base, apply_tail;
-    int32_t allow_mat;          // the pixel kernel has a materialisation chunk (single-source launches)
+    int32_t allow;              // bit 0: the pixel kernel has a materialisation chunk, bit 1: a global scratch image
 };
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 
@@ -33,6 +33,7 @@ struct AugParams {
     const int32_t* partner;     // [B] index into [0, n_all) or nullptr (no mixup)
     const int32_t* order;       // [n_all] LPT schedule written by the resolve kernel, or nullptr
     const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values
+    uint8_t* scratch;           // [n_all][H][W][3] uint8 scratch image for Sharpness->gather programs, or nullptr
     int32_t B, H, W, out_h, out_w;
     int32_t first;              // index of this launch's image 0 inside the n_all arrays
     int32_t use_zero_box;

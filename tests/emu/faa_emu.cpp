@@ -66,14 +66,23 @@ void prepare(const uint8_t* raw, int H, int W, State& st) {
     if (lut_mask == 0) return;
     memset(st.hist, 0, sizeof st.hist);
     st.suml[0] = st.suml[1] = 0;
-    for (int j = 0; j < 2; ++j) {
-        if (!((lut_mask >> j) & 1u)) continue;
-        if ((stat_mask >> j) & 1u) {
-            Ctx c = make_ctx(raw, H, W, st);
-            if (j == 0) accumulate<0>(c, st.prog.op[j].kind, st.hist[0], &st.suml[0]);
-            else accumulate<1>(c, st.prog.op[j].kind, st.hist[1], &st.suml[1]);
+    const int k0 = st.prog.op[0].kind, k1 = st.prog.op[1].kind;
+    const bool push = k0 != K_NONE && kind_is_lutlike(k0) && kind_needs_hist(k1);      // like the kernel
+    Ctx c = make_ctx(raw, H, W, st);
+    if (lut_mask & 1u) {
+        if (kind_needs_hist(k0) || push) accumulate<0>(c, K_EQUALIZE, st.hist[0], &st.suml[0]);
+        if (kind_needs_mean(k0)) accumulate<0>(c, K_CONTRAST, st.hist[0], &st.suml[0]);
+        build_lut(st, 0, H, W);
+    }
+    if (lut_mask & 2u) {
+        if (push) {
+            // raw histogram pushed forward through the first LUT
+            memset(st.hist[1], 0, sizeof st.hist[1]);
+            for (int i = 0; i < 768; ++i) st.hist[1][(i & ~255) + st.lut[0][i]] += st.hist[0][i];
+        } else if ((stat_mask >> 1) & 1u) {
+            accumulate<1>(c, k1, st.hist[1], &st.suml[1]);
         }
-        build_lut(st, j, H, W);
+        build_lut(st, 1, H, W);
     }
     if (st.prog.cls == C_LUT) {
         for (int i = 0; i < 768; ++i) {
@@ -164,7 +173,7 @@ int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W
         for (int k = 0; k < nsrc; ++k) {
             // force_generic: no materialisation / vector classes (the kernel's mixup launches and fallbacks)
             build_prog(samples[src[k]], boxes + (size_t)src[k] * n_op, ops, n_op, op_base, apply_tail, H, W, out_w,
-                       (force_generic || partner) ? 0 : 1, st[k].prog);
+                       (force_generic || partner) ? 0 : 3, st[k].prog);
             if (force_generic) st[k].prog.cls = C_GENERIC;
             const uint8_t* raw = in + img_bytes * src[k];
             t[k] = make_tail(st[k].prog, zb);
@@ -205,7 +214,7 @@ int faa_emu_augment(const uint8_t* in, int n_all, int first, int B, int H, int W
             for (int ox0 = 0; ox0 < out_w; ox0 += 4) {
                 uint32_t px[2][4], zm[2] = {0, 0};
                 for (int k = 0; k < nsrc; ++k) {
-                    if (cls[k] == C_GENERIC || cls[k] == C_GEOM) quad_generic(c[k], t[k], out_w, ox0, oy, px[k]);
+                    if (cls[k] == C_GENERIC || cls[k] == C_GEOM || cls[k] == C_SG) quad_generic(c[k], t[k], out_w, ox0, oy, px[k]);
                     else quad_vec(cls[k], c[k], st[k].lutc, t[k], out_w, ox0, oy, px[k]);
                     zm[k] = zero_mask(t[k], ox0, oy);
                 }
@@ -239,7 +248,7 @@ int faa_emu_classes(const void* ops_v, int n_op, const void* samples_v, const vo
     const Box* boxes = (const Box*)boxes_v;
     for (int i = 0; i < B; ++i) {
         Prog g;
-        build_prog(samples[i], boxes + (size_t)i * n_op, ops, n_op, 0, apply_tail, H, W, out_w, 1, g);
+        build_prog(samples[i], boxes + (size_t)i * n_op, ops, n_op, 0, apply_tail, H, W, out_w, 3, g);
         cls_out[i] = g.cls;
     }
     return 0;
