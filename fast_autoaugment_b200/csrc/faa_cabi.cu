@@ -581,8 +581,10 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (!P.stage) P.band_cap = 0;
     // materialisation chunk: as many rows as fit ~16 KB, at least 3 (single-source launches only)
     {
+        // big enough to keep a whole band (+ halo, + crop slack) resident when that is <= 24 KB, else ~16 KB chunks
         const int pitch = w * 3;
-        int rows = 16384 / pitch;
+        const int band_rows = (h + P.bands - 1) / P.bands + 2 + 2 * P.crop_pad;
+        int rows = (band_rows * pitch <= 24576) ? band_rows : 16384 / pitch;
         if (rows > h + 2) rows = h + 2;
         P.mat_cap = (!mat_off && !d_partner && rows >= 3) ? ((rows * pitch + 32 + 15) & ~15) : 0;   // + 2 guard bands
     }

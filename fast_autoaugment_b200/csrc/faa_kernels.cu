@@ -404,7 +404,9 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
 // coordinate is stepped along the quad instead of being re-derived per pixel
 __device__ __forceinline__ uint32_t load_raw_cg(const Ctx& c, int x, int y) {     // scratch written by this kernel
     const uint8_t* p = c.raw + (uint32_t)(y * c.W + x) * 3u;
-    return (uint32_t)__ldcg(p) | ((uint32_t)__ldcg(p + 1) << 8) | ((uint32_t)__ldcg(p + 2) << 16);
+    // plain weak loads: the cluster barrier that precedes them invalidates L1 (fence scope >= cluster),
+    // so they are coherent with the peers' stores and still L1-cached for the gather's locality
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
 }
 template <bool COH>
 __device__ __forceinline__ void quad_geom(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
@@ -651,14 +653,31 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
     c2.op[1].kind = K_NONE; c2.box[1] = st.prog.box[1];
     c2.lut[0] = st.lut[1]; c2.lut[1] = st.lut[1];
 
+    const TailInfo t = make_tail(P, st.prog);
+    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    // resident mode: every row of op0's output this CTA needs fits the buffer -> evaluate op0 ONCE
+    int ra = min(y0, oy0 + t.crop_dy - halo), rb = max(y1, oy1 + t.crop_dy + halo);
+    if (ra < 0) ra = 0;
+    if (rb > H) rb = H;
+    const bool resident = rb - ra <= rows_cap;
+    if (resident) {
+        fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, ra, rb);
+        c2.s_lo = (uint32_t)ra * pitch - kMatGuard; c2.s_len2 = (uint32_t)(rb - ra) * pitch + 2u * kMatGuard - 2u;
+        __syncthreads();
+    }
     if (stat1) {                                                  // pass A: statistics of op0's output
-        for (int r = y0; r < y1; r += rows_cap) {
-            const int re = min(r + rows_cap, y1);
-            fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, r, re);
-            __syncthreads();
-            c2.s_lo = (uint32_t)r * pitch - kMatGuard; c2.s_len2 = (uint32_t)(re - r) * pitch + 2u * kMatGuard - 2u;
-            accumulate_stats<0>(c2, kind_needs_hist(k1), kind_needs_mean(k1), r, re, st.hist[1], &st.suml[1]);
-            __syncthreads();
+        if (resident) {
+            accumulate_stats<0>(c2, kind_needs_hist(k1), kind_needs_mean(k1), y0, y1, st.hist[1], &st.suml[1]);
+        } else {
+            for (int r = y0; r < y1; r += rows_cap) {
+                const int re = min(r + rows_cap, y1);
+                fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, r, re);
+                __syncthreads();
+                c2.s_lo = (uint32_t)r * pitch - kMatGuard; c2.s_len2 = (uint32_t)(re - r) * pitch + 2u * kMatGuard - 2u;
+                accumulate_stats<0>(c2, kind_needs_hist(k1), kind_needs_mean(k1), r, re, st.hist[1], &st.suml[1]);
+                __syncthreads();
+            }
         }
         exchanged = true;
         const uint32_t mean1 = exchange_stats(P.bands, n_pixels, kind_needs_hist(k1), kind_needs_mean(k1), st, 1, cluster);
@@ -668,22 +687,23 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
             __syncthreads();
         }
     }
-    // pass B: output rows, chunk by chunk
-    const TailInfo t = make_tail(P, st.prog);
-    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    for (int o = oy0; o < oy1; o += step) {
-        const int oe = min(o + step, oy1);
-        int r0 = o + t.crop_dy - halo, r1 = oe + t.crop_dy + halo;          // source rows of this chunk
-        if (r0 < 0) r0 = 0;
-        if (r1 > H) r1 = H;
-        if (r1 > r0) {
-            fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, r0, r1);
-            c2.s_lo = (uint32_t)r0 * pitch - kMatGuard; c2.s_len2 = (uint32_t)(r1 - r0) * pitch + 2u * kMatGuard - 2u;
-        } else { c2.s_lo = 0; c2.s_len2 = 0; }
-        __syncthreads();
-        final_rows_cls<OUT, TAB>(st.prog.cls2, P, s_norm, c2, st.lutc, t, out_img, o, oe);
-        __syncthreads();
+    // pass B: output rows
+    if (resident) {
+        final_rows_cls<OUT, TAB>(st.prog.cls2, P, s_norm, c2, st.lutc, t, out_img, oy0, oy1);
+    } else {
+        for (int o = oy0; o < oy1; o += step) {                   // chunk by chunk
+            const int oe = min(o + step, oy1);
+            int r0 = o + t.crop_dy - halo, r1 = oe + t.crop_dy + halo;      // source rows of this chunk
+            if (r0 < 0) r0 = 0;
+            if (r1 > H) r1 = H;
+            if (r1 > r0) {
+                fill_rows(c0, cls0, st.lut[0], mat + kMatGuard, r0, r1);
+                c2.s_lo = (uint32_t)r0 * pitch - kMatGuard; c2.s_len2 = (uint32_t)(r1 - r0) * pitch + 2u * kMatGuard - 2u;
+            } else { c2.s_lo = 0; c2.s_len2 = 0; }
+            __syncthreads();
+            final_rows_cls<OUT, TAB>(st.prog.cls2, P, s_norm, c2, st.lutc, t, out_img, o, oe);
+            __syncthreads();
+        }
     }
     return exchanged;
 }
@@ -800,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
             Ctx cs = c; cs.op[1].kind = K_NONE;
             fill_rows(cs, C_SHARP, st[0].lut[0], scr + (uint32_t)y0 * (uint32_t)P.W * 3u, y0, y1);
             __threadfence();
-            if (P.bands > 1) cluster.sync(); else __syncthreads();
+            cluster.sync();                                      // also for one band: orders the scratch stores
             Ctx cg2 = c;
             cg2.raw = scr; cg2.s_len2 = 0;
             cg2.op[0] = c.op[1]; cg2.box[0] = c.box[1]; cg2.op[1].kind = K_NONE;
