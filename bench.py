@@ -95,9 +95,11 @@ def cpu_throughput(workload, n_batches, warm_batches, workers):
     # steady-state rate is the same (workers x per-core rate) but a step (= b images) is then
     # one even round over all workers, so a short timed region is not distorted by whole
     # batches that were prefetched before the clock started.
-    task = max(1, b // max(1, workers))
+    task = max(1, b // max(1, min(workers, 16)))  # >= b/16 images per task keeps the main process (IPC) off the critical path
     tasks_per_step = (b + task - 1) // task
-    warm_batches = max(warm_batches, 3)          # >= prefetch depth (2 tasks per worker)
+    # warm-up must cover the prefetch depth (2 tasks per worker) or the timed steps would drain work
+    # that was done before the clock started
+    warm_batches = max(warm_batches, 3, (2 * workers + tasks_per_step - 1) // tasks_per_step + 1)
     ds = _ArrayDataset(arrays, task * tasks_per_step * (n_batches + warm_batches), _cpu_chain(workload))
     torch.set_num_threads(1)
     dl = DataLoader(ds, batch_size=task, shuffle=False, num_workers=workers, drop_last=True,
