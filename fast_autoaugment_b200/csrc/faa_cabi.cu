@@ -577,7 +577,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     static const bool mat_off = [] { const char* e = getenv("FAA_MAT"); return e && e[0] == '0'; }();
     static const bool pdl_off = [] { const char* e = getenv("FAA_PDL"); return e && e[0] == '0'; }();
     P.stage = (!stage_off && img_bytes % 16 == 0 && ((uintptr_t)d_in_all % 16) == 0 &&
-               (size_t)2 * P.band_cap * nsrc <= 150 * 1024) ? 1 : 0;
+               (size_t)P.band_cap * nsrc <= 150 * 1024) ? 1 : 0;
     if (!P.stage) P.band_cap = 0;
     // materialisation chunk: as many rows as fit ~16 KB, at least 3 (single-source launches only)
     {

@@ -41,7 +41,7 @@ namespace faa {
 
 constexpr int kThreads = 256;
 #ifndef FAA_MIN_CTAS
-#define FAA_MIN_CTAS 3
+#define FAA_MIN_CTAS 4
 #endif
 constexpr int kCostBuckets = 8;
 
@@ -118,11 +118,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
 // TMA 1-D bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
-}
-__device__ __forceinline__ void tma_issue(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+__device__ __forceinline__ void tma_stage(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
     const uint32_t b = smem_u32(bar), d = smem_u32(dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
@@ -755,121 +754,91 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
 
 // ---------------------------------------------------------------------------------------
 // launch 2
-constexpr int kSched = 64;       // schedule entries cached in shared memory at a time
-
-// PERSISTENT clusters: cluster c processes the images at schedule slots c, c + n_clusters, ...
-// (the schedule is the resolve kernel's LPT order, so every cluster gets a mix of cost tiers).
-// The raw row band is double buffered: the TMA bulk copy of the NEXT image's band is issued before
-// the current image is evaluated, so its latency (and the order -> program fetch) is hidden.
 template <int OUT, int NSRC, bool TAB>
 __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
-    extern __shared__ __align__(128) uint8_t s_dyn[];           // 2 stages x NSRC row bands, then the materialisation chunk
+    extern __shared__ __align__(128) uint8_t s_dyn[];           // NSRC staged row bands [+ materialisation chunk]
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st[NSRC];
     __shared__ float s_norm[TAB ? 768 : 1];
-    __shared__ __align__(8) uint64_t s_bar[2][NSRC];
-    __shared__ int s_sched[kSched];
+    __shared__ __align__(8) uint64_t s_bar[NSRC];
+    __shared__ int s_img;
 
     const int band = blockIdx.x;
-    const int n_cl = gridDim.y;
-    const int my_n = ((int)P.B - (int)blockIdx.y + n_cl - 1) / n_cl;     // images this cluster processes
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
     uint32_t s_lo = 0, s_len = 0;
     if (P.stage) band_range(band, P.bands, P.H, P.W, P.out_h, P.crop_pad, img_bytes, s_lo, s_len);
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < 2 * NSRC; ++i) mbar_init(&s_bar[0][0] + i);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    const int y0 = (int)(((uint32_t)band * (uint32_t)P.H) / (uint32_t)P.bands);
-    const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.H) / (uint32_t)P.bands);
-    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
-    uint8_t* const mat = s_dyn + (size_t)2 * NSRC * P.band_cap;
 
     // Programmatic dependent launch: everything above overlaps the resolve kernel's tail; the
     // schedule and the programs it writes are only read after this point.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    auto refill = [&](int it0) {     // schedule entries it0 .. it0 + kSched - 1 of this cluster
-        const int it = it0 + (int)threadIdx.x;
-        if (threadIdx.x < kSched && it < my_n) {
-            const int slot = (int)blockIdx.y + it * n_cl;
-            s_sched[threadIdx.x] = P.order ? P.order[P.first + slot] : slot;
-        }
-    };
-    auto issue = [&](int stage, int img) {       // thread 0: TMA the band(s) of image `img` into `stage`
-#pragma unroll
-        for (int s = 0; s < NSRC; ++s) {
-            const int idx = s == 0 ? P.first + img : P.partner[img];
-            tma_issue(&s_bar[stage][s], s_dyn + (size_t)(stage * NSRC + s) * P.band_cap,
-                      P.in + (size_t)idx * img_bytes + s_lo, s_len);
-        }
-    };
-    refill(0);
+    if (threadIdx.x == 0) s_img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
     __syncthreads();
-    if (threadIdx.x == 0 && s_len && my_n > 0) issue(0, s_sched[0]);
+    const int img = s_img;
+    int src_idx[NSRC];
+    src_idx[0] = P.first + img;
+    if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
 
-    for (int it = 0; it < my_n; ++it) {
-        const int stage = it & 1;
-        const int img = s_sched[it & (kSched - 1)];
-        int src_idx[NSRC];
-        src_idx[0] = P.first + img;
-        if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
-        if (it + 1 < my_n) {
-            if (((it + 1) & (kSched - 1)) == 0) { __syncthreads(); refill(it + 1); __syncthreads(); }
-            // stage^1 was last read in iteration it-1, which ended with a block barrier
-            if (threadIdx.x == 0 && s_len) issue(stage ^ 1, s_sched[(it + 1) & (kSched - 1)]);
-        }
-        // per-image programs -> shared memory (24 words each)
+    // 0. stage the raw row band(s): one TMA bulk copy each, in flight while the program loads
+    if (threadIdx.x == 0 && s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s)
-            if (threadIdx.x < sizeof(Prog) / 4)
-                reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
-                    __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
-        __syncthreads();
-        if (s_len) {
-#pragma unroll
-            for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[stage][s], (uint32_t)(it >> 1) & 1u);
-        }
-
-        void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
-        const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
-        const uint8_t* sb0 = s_dyn + (size_t)(stage * NSRC) * P.band_cap;
-        if constexpr (NSRC == 1) {
-            const int cls = st[0].prog.cls;
-            const Ctx c = make_ctx(raw0, sb0, s_lo, s_len, P.H, P.W, st[0], cls != C_PLAIN && cls != C_LUT);
-            if (cls == C_MAT) {
-                run_materialised<OUT, TAB>(P, s_norm, st[0], c, mat, out_img, band, cluster);
-            } else if (cls == C_SG) {
-                // Sharpness then a gather: the band of the sharpened image goes to the global scratch
-                // image, the whole cluster synchronises, then the gather reads scratch
-                uint8_t* scr = P.scratch + (size_t)src_idx[0] * img_bytes;
-                Ctx cs = c; cs.op[1].kind = K_NONE;
-                fill_rows(cs, C_SHARP, st[0].lut[0], scr + (uint32_t)y0 * (uint32_t)P.W * 3u, y0, y1);
-                __threadfence();
-                cluster.sync();                                  // also for one band: orders the scratch stores
-                Ctx cg2 = c;
-                cg2.raw = scr; cg2.s_len2 = 0;
-                cg2.op[0] = c.op[1]; cg2.box[0] = c.box[1]; cg2.op[1].kind = K_NONE;
-                final_rows_cls<OUT, TAB>(C_SG, P, s_norm, cg2, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
-            } else {
-                prepare_image(P, c, y0, y1, st[0], cluster);
-                final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
-            }
-        } else {
-            const uint8_t* raw1 = P.in + (size_t)src_idx[1] * img_bytes;
-            const Ctx c0 = make_ctx(raw0, sb0, s_lo, s_len, P.H, P.W, st[0], true);
-            const Ctx c1 = make_ctx(raw1, sb0 + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
-            prepare_image(P, c0, y0, y1, st[0], cluster);
-            prepare_image(P, c1, y0, y1, st[1], cluster);
-            final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
-        }
-        __syncthreads();       // this stage's band and the image state are free again
+            tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
     }
+    // per-image programs -> shared memory (24 words each)
+#pragma unroll
+    for (int s = 0; s < NSRC; ++s)
+        if (threadIdx.x < sizeof(Prog) / 4)
+            reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
+                __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
+    __syncthreads();
+    if (s_len) {
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
+    }
+
+    const int y0 = (int)(((uint32_t)band * (uint32_t)P.H) / (uint32_t)P.bands);
+    const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.H) / (uint32_t)P.bands);
+    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
+    void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
+    const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
+    bool any_stats = false;
+
+    if constexpr (NSRC == 1) {
+        const int cls = st[0].prog.cls;
+        const Ctx c = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], cls != C_PLAIN && cls != C_LUT);
+        if (cls == C_MAT) {
+            any_stats = run_materialised<OUT, TAB>(P, s_norm, st[0], c, s_dyn + P.band_cap, out_img, band, cluster);
+        } else if (cls == C_SG) {
+            // Sharpness then a gather: the band of the sharpened image goes to the global scratch
+            // image, the whole cluster synchronises, then the gather reads scratch (coherent loads)
+            uint8_t* scr = P.scratch + (size_t)src_idx[0] * img_bytes;
+            Ctx cs = c; cs.op[1].kind = K_NONE;
+            fill_rows(cs, C_SHARP, st[0].lut[0], scr + (uint32_t)y0 * (uint32_t)P.W * 3u, y0, y1);
+            __threadfence();
+            cluster.sync();                                      // also for one band: orders the scratch stores
+            Ctx cg2 = c;
+            cg2.raw = scr; cg2.s_len2 = 0;
+            cg2.op[0] = c.op[1]; cg2.box[0] = c.box[1]; cg2.op[1].kind = K_NONE;
+            final_rows_cls<OUT, TAB>(C_SG, P, s_norm, cg2, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
+        } else {
+            any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
+            final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
+        }
+    } else {
+        const uint8_t* raw1 = P.in + (size_t)src_idx[1] * img_bytes;
+        const Ctx c0 = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], true);
+        const Ctx c1 = make_ctx(raw1, s_dyn + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
+        any_stats = prepare_image(P, c0, y0, y1, st[0], cluster);
+        any_stats |= prepare_image(P, c1, y0, y1, st[1], cluster);
+        final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
+    }
+
+    (void)any_stats;   // statistics exchanges end with their own cluster barrier (build_slot_lut)
 }
 
 // out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math (aug_mixup.py:13-23)
@@ -909,7 +878,7 @@ uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
 
 template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
-    const size_t dyn = (size_t)2 * p.band_cap * NSRC + (size_t)p.mat_cap;
+    const size_t dyn = (size_t)p.band_cap * NSRC + (size_t)p.mat_cap;
     static size_t configured = 0;                   // per instantiation
     if (dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB>,
@@ -918,6 +887,7 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
         configured = dyn;
     }
     cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
@@ -929,20 +899,6 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // overlap with the resolve kernel
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // persistent grid: as many clusters as can be co-resident (cached per shared-memory size / cluster size)
-    static int cached_clusters = 0; static size_t cached_dyn = (size_t)-1; static int cached_bands = 0;
-    if (cached_dyn != dyn || cached_bands != p.bands) {
-        cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.bands * 1024u, 1);
-        int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, faa_augment_kernel<OUT, NSRC, TAB>, &cfg);
-        if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = 1 << 30; }     // fall back: one image per cluster
-        static const int persist_off = [] { const char* v = getenv("FAA_PERSIST"); return (v && v[0] == '0') ? 1 : 0; }();
-        if (persist_off) n = 1 << 30;
-        cached_clusters = n; cached_dyn = dyn; cached_bands = p.bands;
-    }
-    const int n_cl = p.B < cached_clusters ? p.B : cached_clusters;
-    cfg.gridDim = dim3((unsigned)p.bands, (unsigned)n_cl, 1);
     cfg.numAttrs = p.pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
