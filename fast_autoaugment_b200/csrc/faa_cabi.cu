@@ -551,7 +551,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             }
             need = need < 65536 ? 65536 : need * 2;
             CK(cudaMalloc(&p->d_progs, need));
-            CK(cudaMalloc(&p->d_order, need / sizeof(Prog) * sizeof(int32_t) + 16));
+            CK(cudaMalloc(&p->d_order, 2 * (need / sizeof(Prog)) * sizeof(int32_t) + 16));   // order + per-launch counters
             p->d_progs_bytes = need;
         }
     }
@@ -600,6 +600,13 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
     R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = op_base; R.apply_tail = apply_tail;
     R.allow = P.mat_cap > 0 ? 1 : 0;
+    static const bool split_off = [] { const char* e = getenv("FAA_SPLIT"); return e && e[0] == '0'; }();
+    if (P.order != nullptr && !split_off && tail->out_dtype != FAA_U8_HWC) {
+        // light programs run in their own streaming kernel; the counter lives behind the order array,
+        // indexed by `first` so that concurrent chunk launches do not share it
+        int32_t* counters = reinterpret_cast<int32_t*>(p->d_order) + p->d_progs_bytes / sizeof(Prog);
+        R.split = 1; R.n_heavy = counters + first; P.n_heavy = counters + first;
+    }
     if (p->has_sg && !d_partner && (w & 3) == 0) {       // scratch images for Sharpness->gather programs
         const size_t need = (size_t)n_all * img_bytes;
         if (p->d_scratch_bytes < need) {
@@ -616,7 +623,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     g_launches++;
     // launch 2: pixels
     CK(launch_augment(P, tail->out_dtype, use_tab, stream));
-    g_launches++;
+    g_launches += P.n_heavy ? 2 : 1;          // cluster kernel (+ light streaming kernel when split)
     return FAA_OK;
 }
 

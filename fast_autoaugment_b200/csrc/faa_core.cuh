@@ -530,6 +530,12 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
     else g.cls = C_GENERIC;
 }
 
+// "Light" programs need no whole-image statistics and no neighbourhood: they run in the small
+// streaming kernel (no cluster, few registers); everything else runs in the cluster kernel.
+FAA_HD bool prog_is_light(const Prog& g) {
+    return g.stat_mask == 0 && (g.cls == C_PLAIN || g.cls == C_LUT || g.cls == C_POINT || g.cls == C_GEOM);
+}
+
 // Rough relative cost of an image (per-pixel work units) - only used to schedule the
 // expensive images first (longest-processing-time order); never affects results.
 FAA_HD uint32_t op_unit_cost(int k) {

@@ -43,7 +43,7 @@ constexpr int kThreads = 256;
 #ifndef FAA_MIN_CTAS
 #define FAA_MIN_CTAS 4
 #endif
-constexpr int kCostBuckets = 8;
+constexpr int kCostBuckets = 8;       // per weight class; heavy programs sort before light ones
 
 struct __align__(16) ImgState {
     Prog prog;                  // 96 B
@@ -71,10 +71,10 @@ __device__ __forceinline__ int cost_bucket(uint32_t cost) {     // 0 = most expe
 }
 
 __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant__ ResolveParams P) {
-    __shared__ int s_count[kCostBuckets], s_base[kCostBuckets];
+    __shared__ int s_count[2 * kCostBuckets], s_base[2 * kCostBuckets];
     // let the dependent pixel kernel start launching (its prologue overlaps this kernel)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x < kCostBuckets) s_count[threadIdx.x] = 0;
+    if (threadIdx.x < 2 * kCostBuckets) s_count[threadIdx.x] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {
         const int i = P.first + t;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
         if (P.progs != nullptr) {
             Prog g;
             build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, P.allow, g);
-            g.bucket = (uint8_t)cost_bucket(prog_cost(g));
+            g.bucket = (uint8_t)(cost_bucket(prog_cost(g)) + ((P.split && prog_is_light(g)) ? kCostBuckets : 0));
             P.progs[i] = g;
             atomicAdd(&s_count[g.bucket], 1);
         }
@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int b = 0; b < kCostBuckets; ++b) { s_base[b] = acc; acc += s_count[b]; s_count[b] = 0; }
+        for (int b = 0; b < 2 * kCostBuckets; ++b) {
+            if (b == kCostBuckets && P.n_heavy != nullptr) *P.n_heavy = acc;      // images [0, acc) of the order are heavy
+            s_base[b] = acc; acc += s_count[b]; s_count[b] = 0;
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {        // scheduling order only: any order is correct
@@ -774,6 +777,8 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     // schedule and the programs it writes are only read after this point.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule
+    if (P.n_heavy != nullptr && (int)blockIdx.y >= *P.n_heavy) return;      // cluster-uniform
     if (threadIdx.x == 0) s_img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
     __syncthreads();
     const int img = s_img;
@@ -841,6 +846,77 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     (void)any_stats;   // statistics exchanges end with their own cluster barrier (build_slot_lut)
 }
 
+// ---------------------------------------------------------------------------------------
+// launch 3: the streaming kernel for "light" images (no statistics, no neighbourhood ops):
+// PLAIN / LUT / POINT / GEOM classes only - no cluster, 3 KB of static shared memory, a fraction of
+// the cluster kernel's registers and code.  It owns schedule entries [n_heavy, B).
+template <int OUT, bool TAB>
+__global__ void __launch_bounds__(kThreads, 5) faa_augment_light_kernel(const __grid_constant__ AugParams P) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];           // staged row band
+    __shared__ Prog s_prog;
+    __shared__ __align__(16) uint8_t s_lut[2][768];
+    __shared__ __align__(16) uint8_t s_lutc[768];
+    __shared__ float s_norm[TAB ? 768 : 1];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_img;
+
+    const int band = blockIdx.x;
+    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
+    uint32_t s_lo = 0, s_len = 0;
+    if (P.stage) band_range(band, P.bands, P.H, P.W, P.out_h, P.crop_pad, img_bytes, s_lo, s_len);
+    if (TAB)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
+    const int n_heavy = *P.n_heavy;
+    if ((int)blockIdx.y >= P.B - n_heavy) return;
+    if (threadIdx.x == 0) s_img = P.order[P.first + n_heavy + blockIdx.y];
+    __syncthreads();
+    const int img = s_img;
+    const int idx = P.first + img;
+    if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)idx * img_bytes + s_lo, s_len);
+    if (threadIdx.x < sizeof(Prog) / 4)
+        reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
+    __syncthreads();
+    const uint32_t lut_mask = s_prog.lut_mask;
+    if (lut_mask) {                                   // static LUTs only (no statistics in light programs)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if ((lut_mask >> j) & 1u)
+                for (int i = threadIdx.x; i < 768; i += blockDim.x)
+                    s_lut[j][i] = (uint8_t)lut_entry_static(s_prog.op[j], (uint32_t)(i & 255), 0u);
+        __syncthreads();
+        if (s_prog.cls == C_LUT) {
+            for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+                uint32_t v = (uint32_t)(i & 255), base = (uint32_t)(i & ~255);
+                if (lut_mask & 1u) v = s_lut[0][base + v];
+                if (lut_mask & 2u) v = s_lut[1][base + v];
+                s_lutc[i] = (uint8_t)v;
+            }
+            __syncthreads();
+        }
+    }
+    if (s_len) mbar_wait(&s_bar, 0);
+
+    const int cls = s_prog.cls;
+    Ctx c;
+    c.raw = P.in + (size_t)idx * img_bytes; c.sraw = s_dyn; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u;
+    c.H = P.H; c.W = P.W;
+    if (cls == C_POINT || cls == C_GEOM) {
+        c.op[0] = s_prog.op[0]; c.op[1] = s_prog.op[1]; c.box[0] = s_prog.box[0]; c.box[1] = s_prog.box[1];
+    }
+    c.lut[0] = s_lut[0]; c.lut[1] = s_lut[1];
+    const TailInfo t = make_tail(P, s_prog);
+    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
+    void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
+    switch (cls) {
+    case C_PLAIN: final_rows<OUT, TAB, C_PLAIN>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    case C_LUT:   final_rows<OUT, TAB, C_LUT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    default:      final_rows<OUT, TAB, C_GEOM>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    }
+}
+
 // out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math (aug_mixup.py:13-23)
 template <typename T>
 __global__ void faa_mixup_kernel(const T* __restrict__ data, T* __restrict__ out, const int64_t* __restrict__ perm,
@@ -862,7 +938,7 @@ int pick_bands(int H, int W, int out_h, int out_w) {
     int b = 1;
     while (b < 8 && quads / (b * 2) >= 1024 && b * 2 <= H && b * 2 <= out_h) b *= 2;
     const char* e = getenv("FAA_BANDS");          // tuning knob for experiments
-    if (e && *e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) b = (v <= H && v <= out_h) ? v : b; }
+    if (e && *e) { int v = atoi(e); if (v >= 1 && v <= 8) b = (v <= H && v <= out_h) ? v : b; }
     return b;
 }
 
@@ -903,10 +979,26 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
 
+template <int OUT, bool TAB>
+static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
+    const size_t dyn = (size_t)p.band_cap;
+    static size_t configured = 0;
+    if (dyn > configured) {
+        cudaError_t e = cudaFuncSetAttribute(faa_augment_light_kernel<OUT, TAB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        configured = dyn;
+    }
+    faa_augment_light_kernel<OUT, TAB><<<dim3((unsigned)p.bands, (unsigned)p.B, 1), kThreads, dyn, stream>>>(p);
+    return cudaGetLastError();
+}
+
 template <int OUT>
 static cudaError_t launch_out(const AugParams& p, bool mix, bool tab, cudaStream_t stream) {
     if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
-    return tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
+    cudaError_t e = tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
+    if (e != cudaSuccess || p.n_heavy == nullptr) return e;
+    return tab ? launch_light<OUT, true>(p, stream) : launch_light<OUT, false>(p, stream);
 }
 
 cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaStream_t stream) {
@@ -915,8 +1007,8 @@ cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaS
     switch (out_type) {
     case OUT_F16:  return launch_out<OUT_F16>(p, mix, use_tab, stream);
     case OUT_BF16: return launch_out<OUT_BF16>(p, mix, use_tab, stream);
-    case OUT_F32:  return mix ? launch_one<OUT_F32, 2, true>(p, stream) : launch_one<OUT_F32, 1, true>(p, stream);
-    case OUT_U8_HWC: return launch_one<OUT_U8_HWC, 1, false>(p, stream);
+    case OUT_F32:  return launch_out<OUT_F32>(p, mix, true, stream);
+    case OUT_U8_HWC: return launch_out<OUT_U8_HWC>(p, false, false, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -16,6 +16,8 @@ struct ResolveParams {
     const Box* boxes;           // [n][n_op] (may be nullptr when no Cutout box is needed)
     Prog* progs;                // [n] out
     int32_t* order;             // [n] out: local image indices, most expensive first (optional)
+    int32_t* n_heavy;           // out: number of leading order entries that need the cluster kernel (optional)
+    int32_t split;              // sort light programs behind heavy ones (two pixel launches)
     Sample* samples_out;        // optional [n]
     Box* boxes_out;             // optional [n][n_op]
     RngCfg rng;
@@ -32,6 +34,7 @@ struct AugParams {
     const Prog* progs;          // [n_all]
     const int32_t* partner;     // [B] index into [0, n_all) or nullptr (no mixup)
     const int32_t* order;       // [n_all] LPT schedule written by the resolve kernel, or nullptr
+    const int32_t* n_heavy;     // device counter: schedule entries [0, n_heavy) -> cluster kernel, rest -> light kernel; nullptr = no split
     const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values
     uint8_t* scratch;           // [n_all][H][W][3] uint8 scratch image for Sharpness->gather programs, or nullptr
     int32_t B, H, W, out_h, out_w;
