@@ -211,6 +211,7 @@ struct faa_policy {
     void* h_in_stage = nullptr; size_t h_in_bytes = 0;
     void* h_out_stage = nullptr; size_t h_out_bytes = 0;
     cudaStream_t side[2] = {nullptr, nullptr};
+    cudaStream_t light_stream = nullptr; cudaEvent_t ev_res = nullptr, ev_light = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
@@ -300,6 +301,9 @@ int faa_policy_destroy(faa_policy_t* p) {
         if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
     }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->light_stream) cudaStreamDestroy(p->light_stream);
+    if (p->ev_res) cudaEventDestroy(p->ev_res);
+    if (p->ev_light) cudaEventDestroy(p->ev_light);
     delete p;
     return FAA_OK;
 }
@@ -622,8 +626,24 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     CK(launch_resolve(R, stream));
     g_launches++;
     // launch 2: pixels
-    CK(launch_augment(P, tail->out_dtype, use_tab, stream));
-    g_launches += P.n_heavy ? 2 : 1;          // cluster kernel (+ light streaming kernel when split)
+    if (P.n_heavy) {
+        // the light streaming kernel runs CONCURRENTLY with the cluster kernel on a side stream
+        if (!p->light_stream) {
+            CK(cudaStreamCreateWithFlags(&p->light_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->ev_light, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(p->ev_res, stream));
+        CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
+        CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
+        CK(launch_augment(P, tail->out_dtype, use_tab, true, p->light_stream));
+        CK(cudaEventRecord(p->ev_light, p->light_stream));
+        CK(cudaStreamWaitEvent(stream, p->ev_light, 0));
+        g_launches += 2;
+    } else {
+        CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
+        g_launches++;
+    }
     return FAA_OK;
 }
 

@@ -994,21 +994,22 @@ static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
 }
 
 template <int OUT>
-static cudaError_t launch_out(const AugParams& p, bool mix, bool tab, cudaStream_t stream) {
+static cudaError_t launch_out(const AugParams& p, bool mix, bool tab, bool light, cudaStream_t stream) {
+    if (light) return tab ? launch_light<OUT, true>(p, stream) : launch_light<OUT, false>(p, stream);
     if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
-    cudaError_t e = tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
-    if (e != cudaSuccess || p.n_heavy == nullptr) return e;
-    return tab ? launch_light<OUT, true>(p, stream) : launch_light<OUT, false>(p, stream);
+    return tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
 }
 
-cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaStream_t stream) {
+// light == false: the cluster kernel (all images, or the heavy part of a split launch);
+// light == true : the streaming kernel for the light part of a split launch (p.n_heavy != nullptr)
+cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, bool light, cudaStream_t stream) {
     if (p.B <= 0) return cudaSuccess;
     const bool mix = p.partner != nullptr;
     switch (out_type) {
-    case OUT_F16:  return launch_out<OUT_F16>(p, mix, use_tab, stream);
-    case OUT_BF16: return launch_out<OUT_BF16>(p, mix, use_tab, stream);
-    case OUT_F32:  return launch_out<OUT_F32>(p, mix, true, stream);
-    case OUT_U8_HWC: return launch_out<OUT_U8_HWC>(p, false, false, stream);
+    case OUT_F16:  return launch_out<OUT_F16>(p, mix, use_tab, light, stream);
+    case OUT_BF16: return launch_out<OUT_BF16>(p, mix, use_tab, light, stream);
+    case OUT_F32:  return launch_out<OUT_F32>(p, mix, true, light, stream);
+    case OUT_U8_HWC: return launch_out<OUT_U8_HWC>(p, false, false, light, stream);
     default: return cudaErrorInvalidValue;
     }
 }

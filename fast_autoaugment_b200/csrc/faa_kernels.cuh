@@ -49,7 +49,7 @@ struct AugParams {
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };
-cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, cudaStream_t stream);
+cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, bool light, cudaStream_t stream);
 
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,
                          int dtype, float lam, float one_minus_lam, cudaStream_t stream);
