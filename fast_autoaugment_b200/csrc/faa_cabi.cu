@@ -583,6 +583,15 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     P.stage = (!stage_off && img_bytes % 16 == 0 && ((uintptr_t)d_in_all % 16) == 0 &&
                (size_t)P.band_cap * nsrc <= 150 * 1024) ? 1 : 0;
     if (!P.stage) P.band_cap = 0;
+    {   // per-kernel band geometry and fastdiv reciprocals (host side: no divisions in the kernels)
+        fill_geom(P.geo[0], P.bands, h, w, tail->out_h, P.crop_pad, P.stage != 0);
+        int lb = P.bands;
+        static const int light_bands = [] { const char* e = getenv("FAA_LIGHT_BANDS"); return e ? atoi(e) : 0; }();
+        if (light_bands >= 1 && light_bands <= 8 && light_bands <= h && light_bands <= tail->out_h) lb = light_bands;
+        fill_geom(P.geo[1], lb, h, w, tail->out_h, P.crop_pad, P.stage != 0 && (size_t)band_capacity(lb, h, w, tail->out_h, P.crop_pad) <= 100 * 1024);
+        auto rcp = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); };
+        P.rcp_out_qpr = rcp((uint32_t)(tail->out_w + 3) / 4); P.rcp_w = rcp((uint32_t)w); P.rcp_wq = rcp((uint32_t)w / 4);
+    }
     // materialisation chunk: as many rows as fit ~16 KB, at least 3 (single-source launches only)
     {
         // big enough to keep a whole band (+ halo, + crop slack) resident when that is <= 24 KB, else ~16 KB chunks

@@ -42,7 +42,7 @@ enum Kind : int32_t {
     K_CUTOUT = 10        // a[0..1]=fp64 bits of the side length in pixels; box comes per sample
 };
 
-struct OpRec {           // 32 bytes, one per (sub-policy, op slot, sign variant)
+struct alignas(16) OpRec {  // 32 bytes, one per (sub-policy, op slot, sign variant)
     int32_t kind;
     int32_t a[6];
     int32_t draw;        // enum faa_draw of the *named* op (kept even when kind==K_NONE)
@@ -143,6 +143,7 @@ struct Ctx {
     const uint8_t* raw;      // this image, uint8 HWC (global memory)
     const uint8_t* sraw;     // TMA-staged copy of bytes [s_lo, s_lo + s_len) of the image (shared memory)
     uint32_t s_lo, s_len2;   // s_len2 = staged length - 2 (0 when nothing is staged)
+    uint32_t rcp_w, rcp_wq;  // fastdiv reciprocals of W and W/4 (device loops)
     int H, W;
     OpRec op[2];             // the two fused op slots (K_NONE when not applied)
     Box box[2];              // clipped inclusive Cutout boxes (valid when op[j].kind==K_CUTOUT)
@@ -458,7 +459,7 @@ enum ProgClass : uint8_t {
                      // shared memory and op1 runs on it as a single-op program of class `cls2`
 };
 
-struct Prog {        // 96 bytes
+struct alignas(16) Prog {   // 96 bytes (moved with 128-bit loads / stores)
     OpRec op[2];
     Box box[2];
     int16_t zero_box[4];

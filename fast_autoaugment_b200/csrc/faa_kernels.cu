@@ -32,6 +32,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "faa_kernels.cuh"
 
@@ -57,7 +58,7 @@ struct __align__(16) ImgState {
 
 struct FastDiv {
     uint32_t d, rcp;
-    __device__ __forceinline__ void init(uint32_t dd) { d = dd; rcp = recip32(dd); }
+    __device__ __forceinline__ void init(uint32_t dd, uint32_t r) { d = dd; rcp = r; }     // r = recip32(dd), from the host
     __device__ __forceinline__ uint32_t div(uint32_t q) const { return d == 1u ? q : fastdiv(q, rcp); }
 };
 
@@ -157,9 +158,10 @@ __host__ __device__ inline void band_range(int band, int bands, int H, int W, in
 }
 
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ Ctx make_ctx(const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo, uint32_t s_len,
+__device__ __forceinline__ Ctx make_ctx(const AugParams& P, const uint8_t* raw, const uint8_t* sraw, uint32_t s_lo, uint32_t s_len,
                                         int H, int W, const ImgState& st, bool full) {
     Ctx c;
+    c.rcp_w = P.rcp_w; c.rcp_wq = P.rcp_wq;
     c.raw = raw; c.sraw = sraw; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u; c.H = H; c.W = W;
     if (full) {
         c.op[0] = st.prog.op[0]; c.op[1] = st.prog.op[1];
@@ -223,7 +225,7 @@ __device__ void accumulate_stats(const Ctx& c, bool want_hist, bool want_mean, i
         }
     } else {
         const uint32_t n = (uint32_t)(y1 - y0) * (uint32_t)c.W;
-        FastDiv dw; dw.init((uint32_t)c.W);
+        FastDiv dw; dw.init((uint32_t)c.W, c.rcp_w);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             uint32_t r = dw.div(i);
             uint32_t p = Level<L>::at(c, (int)(i - r * c.W), y0 + (int)r);
@@ -533,7 +535,7 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
                                            const TailInfo& t, void* out_img, int oy0, int oy1) {
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
     const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
-    FastDiv dq; dq.init(qpr);
+    FastDiv dq; dq.init(qpr, P.rcp_out_qpr);
     const bool vec = (P.out_w & 3) == 0;
     // incremental (row, quad) walk: one division up front, adds afterwards
     uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
@@ -579,7 +581,7 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
     const int W = c.W;
     if ((W & 3) == 0) {
         const uint32_t qpr = (uint32_t)W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
-        FastDiv dq; dq.init(qpr);
+        FastDiv dq; dq.init(qpr, c.rcp_wq);
         TailInfo id; id.crop_dy = id.crop_dx = id.flip = 0; id.zb0 = id.zb1 = id.zb2 = id.zb3 = 0;
         for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
             const uint32_t r = dq.div(q);
@@ -601,7 +603,7 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
         }
     } else {
         const uint32_t n = (uint32_t)(r1 - r0) * (uint32_t)W;
-        FastDiv dw; dw.init((uint32_t)W);
+        FastDiv dw; dw.init((uint32_t)W, c.rcp_w);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t r = dw.div(i);
             const uint32_t p = Level<1>::at(c, (int)(i - r * W), r0 + (int)r);
@@ -629,8 +631,7 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
     const int halo = (k1 == K_SHARPNESS) ? 1 : 0;
     const int rows_cap = (P.mat_cap - 2 * (int)kMatGuard) / (int)pitch;      // >= 3
     const int step = rows_cap - 2 * halo;
-    const int y0 = (int)(((uint32_t)band * (uint32_t)H) / (uint32_t)P.bands);
-    const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)H) / (uint32_t)P.bands);
+    const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
     bool exchanged = false;
 
     // op0's own LUT (and statistics over the raw band) first
@@ -651,14 +652,13 @@ __device__ bool run_materialised(const AugParams& P, const float* s_norm, ImgSta
     const int cls0 = single_op_class(k0, W);
     // the op1-only program that runs on the materialised rows
     Ctx c2;
-    c2.raw = nullptr; c2.sraw = mat; c2.H = H; c2.W = W;
+    c2.raw = nullptr; c2.sraw = mat; c2.H = H; c2.W = W; c2.rcp_w = c.rcp_w; c2.rcp_wq = c.rcp_wq;
     c2.op[0] = st.prog.op[1]; c2.box[0] = st.prog.box[1];
     c2.op[1].kind = K_NONE; c2.box[1] = st.prog.box[1];
     c2.lut[0] = st.lut[1]; c2.lut[1] = st.lut[1];
 
     const TailInfo t = make_tail(P, st.prog);
-    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
     // resident mode: every row of op0's output this CTA needs fits the buffer -> evaluate op0 ONCE
     int ra = min(y0, oy0 + t.crop_dy - halo), rb = max(y1, oy1 + t.crop_dy + halo);
     if (ra < 0) ra = 0;
@@ -716,11 +716,10 @@ template <int OUT, bool TAB>
 __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const ImgState* st, const Ctx& c0,
                                const Ctx& c1, void* out_img, int band) {
     using T = typename OutElem<OUT>::T;
-    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
     const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
-    FastDiv dq; dq.init(qpr);
+    FastDiv dq; dq.init(qpr, P.rcp_out_qpr);
     const bool vec = (P.out_w & 3) == 0;
     const TailInfo t0 = make_tail(P, st[0].prog), t1 = make_tail(P, st[1].prog);
     const int cls0 = st[0].prog.cls, cls1 = st[1].prog.cls;
@@ -768,8 +767,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
 
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
-    uint32_t s_lo = 0, s_len = 0;
-    if (P.stage) band_range(band, P.bands, P.H, P.W, P.out_h, P.crop_pad, img_bytes, s_lo, s_len);
+    const uint32_t s_lo = P.geo[0].lo[band], s_len = P.geo[0].len[band];
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
 
@@ -804,10 +802,8 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
         for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
     }
 
-    const int y0 = (int)(((uint32_t)band * (uint32_t)P.H) / (uint32_t)P.bands);
-    const int y1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.H) / (uint32_t)P.bands);
-    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
+    const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
     const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
@@ -815,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
 
     if constexpr (NSRC == 1) {
         const int cls = st[0].prog.cls;
-        const Ctx c = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], cls != C_PLAIN && cls != C_LUT);
+        const Ctx c = make_ctx(P, raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], cls != C_PLAIN && cls != C_LUT);
         if (cls == C_MAT) {
             any_stats = run_materialised<OUT, TAB>(P, s_norm, st[0], c, s_dyn + P.band_cap, out_img, band, cluster);
         } else if (cls == C_SG) {
@@ -836,8 +832,8 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
         }
     } else {
         const uint8_t* raw1 = P.in + (size_t)src_idx[1] * img_bytes;
-        const Ctx c0 = make_ctx(raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], true);
-        const Ctx c1 = make_ctx(raw1, s_dyn + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
+        const Ctx c0 = make_ctx(P, raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], true);
+        const Ctx c1 = make_ctx(P, raw1, s_dyn + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
         any_stats = prepare_image(P, c0, y0, y1, st[0], cluster);
         any_stats |= prepare_image(P, c1, y0, y1, st[1], cluster);
         final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
@@ -862,8 +858,7 @@ __global__ void __launch_bounds__(kThreads, 5) faa_augment_light_kernel(const __
 
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
-    uint32_t s_lo = 0, s_len = 0;
-    if (P.stage) band_range(band, P.bands, P.H, P.W, P.out_h, P.crop_pad, img_bytes, s_lo, s_len);
+    const uint32_t s_lo = P.geo[1].lo[band], s_len = P.geo[1].len[band];
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     const int n_heavy = *P.n_heavy;
@@ -899,14 +894,13 @@ __global__ void __launch_bounds__(kThreads, 5) faa_augment_light_kernel(const __
     const int cls = s_prog.cls;
     Ctx c;
     c.raw = P.in + (size_t)idx * img_bytes; c.sraw = s_dyn; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u;
-    c.H = P.H; c.W = P.W;
+    c.H = P.H; c.W = P.W; c.rcp_w = P.rcp_w; c.rcp_wq = P.rcp_wq;
     if (cls == C_POINT || cls == C_GEOM) {
         c.op[0] = s_prog.op[0]; c.op[1] = s_prog.op[1]; c.box[0] = s_prog.box[0]; c.box[1] = s_prog.box[1];
     }
     c.lut[0] = s_lut[0]; c.lut[1] = s_lut[1];
     const TailInfo t = make_tail(P, s_prog);
-    const int oy0 = (int)(((uint32_t)band * (uint32_t)P.out_h) / (uint32_t)P.bands);
-    const int oy1 = (int)(((uint32_t)(band + 1) * (uint32_t)P.out_h) / (uint32_t)P.bands);
+    const int oy0 = P.geo[1].oy[band], oy1 = P.geo[1].oy[band + 1];
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
     switch (cls) {
@@ -942,6 +936,21 @@ int pick_bands(int H, int W, int out_h, int out_w) {
     return b;
 }
 
+void fill_geom(BandGeom& g, int bands, int H, int W, int out_h, int crop_pad, bool stage) {
+    memset(&g, 0, sizeof g);
+    g.bands = bands;
+    uint32_t cap = 0;
+    for (int b = 0; b <= bands; ++b) {
+        g.y[b] = (int32_t)((uint32_t)(b * H) / (uint32_t)bands);
+        g.oy[b] = (int32_t)((uint32_t)(b * out_h) / (uint32_t)bands);
+    }
+    for (int b = 0; b < bands && stage; ++b) {
+        band_range(b, bands, H, W, out_h, crop_pad, (uint32_t)H * (uint32_t)W * 3u, g.lo[b], g.len[b]);
+        if (g.len[b] > cap) cap = g.len[b];
+    }
+    g.band_cap = (int32_t)((cap + 127u) & ~127u);
+}
+
 uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
     uint32_t cap = 0;
     for (int b = 0; b < bands; ++b) {
@@ -954,7 +963,7 @@ uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
 
 template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
-    const size_t dyn = (size_t)p.band_cap * NSRC + (size_t)p.mat_cap;
+    const size_t dyn = (size_t)p.geo[0].band_cap * NSRC + (size_t)p.mat_cap;
     static size_t configured = 0;                   // per instantiation
     if (dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB>,
@@ -981,7 +990,7 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
 
 template <int OUT, bool TAB>
 static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
-    const size_t dyn = (size_t)p.band_cap;
+    const size_t dyn = (size_t)p.geo[1].band_cap;
     static size_t configured = 0;
     if (dyn > configured) {
         cudaError_t e = cudaFuncSetAttribute(faa_augment_light_kernel<OUT, TAB>,
@@ -989,7 +998,7 @@ static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         configured = dyn;
     }
-    faa_augment_light_kernel<OUT, TAB><<<dim3((unsigned)p.bands, (unsigned)p.B, 1), kThreads, dyn, stream>>>(p);
+    faa_augment_light_kernel<OUT, TAB><<<dim3((unsigned)p.geo[1].bands, (unsigned)p.B, 1), kThreads, dyn, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,15 @@ struct ResolveParams {
 };
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 
+// row-band geometry of a pixel launch, precomputed on the host (no divisions in the kernels)
+struct BandGeom {
+    int32_t bands;              // CTAs per image
+    int32_t band_cap;           // bytes of dynamic shared memory per staged band (0: staging off)
+    int32_t y[9];               // band b owns image rows [y[b], y[b+1]) for whole-image statistics
+    int32_t oy[9];              // ... and output rows [oy[b], oy[b+1])
+    uint32_t lo[8], len[8];     // staged byte range of the raw image per band (len 0: nothing staged)
+};
+
 // step 2 (one cluster per image): pixels
 struct AugParams {
     const uint8_t* in;          // [n_all][H][W][3] uint8
@@ -40,7 +49,9 @@ struct AugParams {
     int32_t B, H, W, out_h, out_w;
     int32_t first;              // index of this launch's image 0 inside the n_all arrays
     int32_t use_zero_box;
-    int32_t bands;              // CTAs (== cluster size) per image
+    int32_t bands;              // CTAs (== cluster size) per image of the cluster kernel (== geo[0].bands)
+    BandGeom geo[2];            // [0] cluster kernel, [1] light streaming kernel
+    uint32_t rcp_out_qpr, rcp_w, rcp_wq;   // 2^32 / ceil(out_w/4), 2^32 / W, 2^32 / (W/4)  (rounded up) for fastdiv
     int32_t stage;              // 1: TMA-stage the raw row band into shared memory
     int32_t band_cap;           // bytes of dynamic shared memory per staged band
     int32_t crop_pad;           // max |crop_dy| (RandomCrop padding)
@@ -55,6 +66,7 @@ cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int b
                          int dtype, float lam, float one_minus_lam, cudaStream_t stream);
 
 int pick_bands(int H, int W, int out_h, int out_w);
+void fill_geom(BandGeom& g, int bands, int H, int W, int out_h, int crop_pad, bool stage);
 uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad);
 
 }  // namespace faa
