@@ -203,7 +203,13 @@ struct faa_policy {
     float norm_host[768];
     // scratch of faa_augment_host
     void* d_progs = nullptr; size_t d_progs_bytes = 0;
-    void* d_order = nullptr;             // int32 [capacity of d_progs in images]
+    void* d_order = nullptr;             // int32 [capacity of d_progs in images] (+ counters), two slots like d_progs
+    // resolve-ahead: the decisions of the NEXT batch are resolved on a side stream while this batch's
+    // pixels are computed; a call whose (rng, shapes, ...) key matches the speculation skips its resolve launch
+    struct AheadKey { uint64_t seed, first_index; int32_t v[16]; };
+    AheadKey ahead_key{}; bool ahead_valid = false; int ahead_slot = 0, cur_slot = 0;
+    uint64_t last_first_index = 0; bool have_last = false; AheadKey last_key{};
+    cudaStream_t ahead_stream = nullptr; cudaEvent_t ev_ahead = nullptr;
     void* d_scratch = nullptr; size_t d_scratch_bytes = 0;   // Sharpness->gather scratch images
     bool has_sg = false;                 // some sub-policy has Sharpness followed by a geometric op
     void* d_in = nullptr; size_t d_in_bytes = 0;
@@ -302,6 +308,8 @@ int faa_policy_destroy(faa_policy_t* p) {
     }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->light_stream) cudaStreamDestroy(p->light_stream);
+    if (p->ahead_stream) cudaStreamDestroy(p->ahead_stream);
+    if (p->ev_ahead) cudaEventDestroy(p->ev_ahead);
     if (p->ev_res) cudaEventDestroy(p->ev_res);
     if (p->ev_light) cudaEventDestroy(p->ev_light);
     delete p;
@@ -530,7 +538,7 @@ int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t
 static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch,
                           int h, int w, const faa_tail_t* tail, const faa_sample_t* d_samples,
                           const faa_box_t* d_boxes, const faa_rng_t* rng, int op_base, const int32_t* d_partner,
-                          float lam, float oml, int apply_tail, void* stream_v) {
+                          float lam, float oml, int apply_tail, bool allow_ahead, void* stream_v) {
     if (!p || (!d_in_all && batch > 0) || (!d_out && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
     if (batch < 0 || first < 0 || first + batch > n_all) return fail(FAA_ERR_VALUE, "bad batch range");
     if (int e = check_shape(h, w)) return e;
@@ -550,25 +558,26 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         if (p->d_progs_bytes < need) {
             if (p->d_progs) {
                 CK(cudaStreamSynchronize(stream));
+                if (p->ahead_stream) CK(cudaStreamSynchronize(p->ahead_stream));
                 CK(cudaFree(p->d_progs)); CK(cudaFree(p->d_order));
                 p->d_progs = p->d_order = nullptr; p->d_progs_bytes = 0;
             }
             need = need < 65536 ? 65536 : need * 2;
-            CK(cudaMalloc(&p->d_progs, need));
-            CK(cudaMalloc(&p->d_order, 2 * (need / sizeof(Prog)) * sizeof(int32_t) + 16));   // order + per-launch counters
+            CK(cudaMalloc(&p->d_progs, 2 * need));                                                // two slots (resolve-ahead)
+            CK(cudaMalloc(&p->d_order, 2 * (2 * (need / sizeof(Prog)) * sizeof(int32_t) + 16)));  // order + per-launch counters, x2
             p->d_progs_bytes = need;
+            p->ahead_valid = false;
         }
     }
     // geometry of the pixel launch (needed by the resolve step: allow_mat)
     AugParams P; memset(&P, 0, sizeof P);
-    P.in = d_in_all; P.out = d_out; P.progs = reinterpret_cast<const Prog*>(p->d_progs);
+    P.in = d_in_all; P.out = d_out;
     P.partner = d_partner;
     P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.first = first;
     P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
     P.lam = lam; P.one_minus_lam = oml;
     P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
     static const bool lpt_off = [] { const char* e = getenv("FAA_LPT"); return e && e[0] == '0'; }();
-    P.order = (d_partner || lpt_off) ? nullptr : reinterpret_cast<const int32_t*>(p->d_order);
     // TMA band staging needs 16-byte aligned image bases and a band that fits shared memory
     // (crop_pad only sizes the staged band; rows outside it are read from global memory)
     P.crop_pad = tail->crop_pad > 0 ? tail->crop_pad : 0;
@@ -606,20 +615,27 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     ResolveParams R; memset(&R, 0, sizeof R);
     R.ops = d_ops; R.probs = p->d_probs;
     R.samples = reinterpret_cast<const Sample*>(d_samples); R.boxes = reinterpret_cast<const Box*>(d_boxes);
-    R.progs = reinterpret_cast<Prog*>(p->d_progs);
-    R.order = d_partner ? nullptr : reinterpret_cast<int32_t*>(p->d_order);
     if (rng) memcpy(&R.rng, rng, sizeof(RngCfg));
     R.first = d_partner ? 0 : first; R.n = d_partner ? n_all : batch;
     R.H = h; R.W = w; R.out_h = tail->out_h; R.out_w = tail->out_w;
     R.n_sub = p->n_sub; R.n_op = p->n_op; R.op_base = op_base; R.apply_tail = apply_tail;
     R.allow = P.mat_cap > 0 ? 1 : 0;
     static const bool split_off = [] { const char* e = getenv("FAA_SPLIT"); return e && e[0] == '0'; }();
-    if (P.order != nullptr && !split_off && tail->out_dtype != FAA_U8_HWC) {
-        // light programs run in their own streaming kernel; the counter lives behind the order array,
+    static const bool ahead_off = [] { const char* e = getenv("FAA_AHEAD"); return e && e[0] == '0'; }();
+    const bool use_order = !(d_partner || lpt_off);
+    const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC;
+    R.split = use_split ? 1 : 0;
+    // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[cap]
+    const size_t cap_imgs = p->d_progs_bytes / sizeof(Prog);
+    auto bind_slot = [&](int slot, ResolveParams& r, AugParams* a) {
+        Prog* progs = reinterpret_cast<Prog*>((uint8_t*)p->d_progs + (size_t)slot * p->d_progs_bytes);
+        int32_t* order = reinterpret_cast<int32_t*>(p->d_order) + (size_t)slot * (2 * cap_imgs + 4);
+        // light programs run in their own streaming kernel; its counter lives behind the order array,
         // indexed by `first` so that concurrent chunk launches do not share it
-        int32_t* counters = reinterpret_cast<int32_t*>(p->d_order) + p->d_progs_bytes / sizeof(Prog);
-        R.split = 1; R.n_heavy = counters + first; P.n_heavy = counters + first;
-    }
+        int32_t* counter = order + cap_imgs + first;
+        r.progs = progs; r.order = use_order ? order : nullptr; r.n_heavy = use_split ? counter : nullptr;
+        if (a) { a->progs = progs; a->order = use_order ? order : nullptr; a->n_heavy = use_split ? counter : nullptr; }
+    };
     if (p->has_sg && !d_partner && (w & 3) == 0) {       // scratch images for Sharpness->gather programs
         const size_t need = (size_t)n_all * img_bytes;
         if (p->d_scratch_bytes < need) {
@@ -632,17 +648,60 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     }
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
-    CK(launch_resolve(R, stream));
-    g_launches++;
+    // resolve-ahead: did the previous call already resolve exactly this batch on the side stream?
+    const bool spec_ok = allow_ahead && !ahead_off && rng && !d_samples && !d_partner;
+    faa_policy::AheadKey key; memset(&key, 0, sizeof key);
+    if (spec_ok) {
+        key.seed = rng->seed; key.first_index = rng->first_index;
+        const int32_t v[16] = {batch, n_all, first, h, w, tail->out_h, tail->out_w, op_base, apply_tail, R.allow, R.split,
+                               rng->crop_pad, rng->hflip, rng->zero_box_len, use_order ? 1 : 0, 0};
+        memcpy(key.v, v, sizeof v);
+    }
+    const bool hit = spec_ok && p->ahead_valid && memcmp(&key, &p->ahead_key, sizeof key) == 0;
+    int slot = p->cur_slot;
+    if (hit) {
+        slot = p->ahead_slot;
+        CK(cudaStreamWaitEvent(stream, p->ev_ahead, 0));
+        P.pdl = 0;                                          // no resolve kernel right in front of the pixel kernel
+        bind_slot(slot, R, &P);
+    } else {
+        bind_slot(slot, R, &P);
+        CK(launch_resolve(R, stream));
+        g_launches++;
+    }
+    p->cur_slot = slot;
+    p->ahead_valid = false;
+    if (P.n_heavy || spec_ok) {
+        if (!p->light_stream) {
+            CK(cudaStreamCreateWithFlags(&p->light_stream, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&p->ahead_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->ev_light, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->ev_ahead, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(p->ev_res, stream));               // this batch's programs are ready
+    }
+    if (spec_ok) {
+        // speculate on the next call: same everything, first_index advanced by the stride seen so far
+        uint64_t stride = (uint64_t)batch;
+        faa_policy::AheadKey base = key; base.first_index = 0;
+        faa_policy::AheadKey lastb = p->last_key; lastb.first_index = 0;
+        if (p->have_last && memcmp(&base, &lastb, sizeof base) == 0 && rng->first_index > p->last_key.first_index)
+            stride = rng->first_index - p->last_key.first_index;
+        p->last_key = key; p->have_last = true;
+        ResolveParams R2 = R;
+        R2.rng.first_index = rng->first_index + stride;
+        bind_slot(slot ^ 1, R2, nullptr);
+        CK(cudaStreamWaitEvent(p->ahead_stream, p->ev_res, 0));      // the other slot's last readers are done
+        CK(launch_resolve(R2, p->ahead_stream));
+        CK(cudaEventRecord(p->ev_ahead, p->ahead_stream));
+        g_launches++;
+        p->ahead_key = key; p->ahead_key.first_index = rng->first_index + stride;
+        p->ahead_slot = slot ^ 1; p->ahead_valid = true;
+    }
     // launch 2: pixels
     if (P.n_heavy) {
         // the light streaming kernel runs CONCURRENTLY with the cluster kernel on a side stream
-        if (!p->light_stream) {
-            CK(cudaStreamCreateWithFlags(&p->light_stream, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&p->ev_light, cudaEventDisableTiming));
-        }
-        CK(cudaEventRecord(p->ev_res, stream));
         CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
         CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
         CK(launch_augment(P, tail->out_dtype, use_tab, true, p->light_stream));
@@ -665,7 +724,7 @@ int faa_augment(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, in
     if (!apply_tail && tail && (tail->out_dtype != FAA_U8_HWC || tail->out_h != h || tail->out_w != w))
         return fail(FAA_ERR_VALUE, "intermediate launches of a chained policy must write uint8 HWC at the input size");
     return augment_common(p, d_in, batch, 0, d_out, batch, h, w, tail, d_samples, d_boxes, rng, op_base, nullptr,
-                          1.0f, 0.0f, apply_tail, stream);
+                          1.0f, 0.0f, apply_tail, p->n_op <= FAA_MAX_FUSED_OPS, stream);
 }
 
 int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch, int h,
@@ -675,7 +734,7 @@ int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int f
     if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "fused mixup supports policies of at most 2 ops");
     if (!(lam >= 0.0f && lam <= 1.0f)) return fail(FAA_ERR_MAGNITUDE, "lam must be in [0, 1]");   // aug_mixup.py:20
     return augment_common(p, d_in_all, n_all, first, d_out, batch, h, w, tail, d_samples_all, d_boxes_all, rng, 0,
-                          d_partner, lam, one_minus_lam, 1, stream);
+                          d_partner, lam, one_minus_lam, 1, false, stream);
 }
 
 int faa_mixup(const void* d_data, void* d_out, const int64_t* d_perm, int batch, int64_t n_per_sample, int dtype,
@@ -765,7 +824,7 @@ int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_
         cudaStream_t s = p->side[c & 1];
         CK(cudaMemcpyAsync((uint8_t*)p->d_in + in_img * b0, src + in_img * b0, in_img * (b1 - b0), cudaMemcpyHostToDevice, s));
         if (int e = augment_common(p, (const uint8_t*)p->d_in, batch, b0, (uint8_t*)d_out + out_img * b0, b1 - b0, h, w,
-                                   tail, nullptr, nullptr, rng, 0, nullptr, 1.0f, 0.0f, 1, s)) return e;
+                                   tail, nullptr, nullptr, rng, 0, nullptr, 1.0f, 0.0f, 1, false, s)) return e;
         if (dst) CK(cudaMemcpyAsync((uint8_t*)dst + out_img * b0, (uint8_t*)d_out + out_img * b0, out_img * (b1 - b0), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < 2; ++i) {
