@@ -7,8 +7,6 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
-#include <algorithm>
-#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -199,7 +197,6 @@ struct faa_policy {
     std::mutex mu;
     std::map<std::pair<int, int>, std::vector<Compiled>> host_tables;   // (H,W) -> [n_sub][n_op][2]
     std::map<std::pair<int, int>, DeviceTable> dev_tables;
-    std::map<std::array<int, 8>, double> share_cache;     // heavy-work share per launch geometry
     double* d_probs = nullptr;
     float* d_norm = nullptr;            // [3][256]
     float norm_mean[3] = {-1e30f, 0, 0}, norm_std[3] = {0, 0, 0};
@@ -224,12 +221,8 @@ struct faa_policy {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
-static const std::vector<Compiled>& host_table_nolock(faa_policy* p, int H, int W);
 static const std::vector<Compiled>& host_table(faa_policy* p, int H, int W) {
     std::lock_guard<std::mutex> lk(p->mu);
-    return host_table_nolock(p, H, W);
-}
-static const std::vector<Compiled>& host_table_nolock(faa_policy* p, int H, int W) {
     auto key = std::make_pair(H, W);
     auto it = p->host_tables.find(key);
     if (it != p->host_tables.end()) return it->second;
@@ -434,36 +427,6 @@ int faa_sample_policy_mt(const faa_policy_t* pc, int batch, int h, int w, uint32
         out_samples[i] = s;
     }
     return FAA_OK;
-}
-
-// Expected share of the pixel work that falls on "heavy" programs (cluster kernel) for this policy:
-// exact over sub-policies and gate combinations, weighted with the scheduler's cost model.
-static double heavy_share(faa_policy* p, const std::vector<Compiled>& t, int H, int W, int out_w, int allow, int op_base,
-                          int apply_tail) {
-    std::vector<OpRec> flat(t.size());
-    for (size_t i = 0; i < t.size(); ++i) flat[i] = t[i].rec;
-    double heavy = 0.0, total = 0.0;
-    Box boxes[FAA_MAX_POLICY_OPS];
-    for (int j = 0; j < FAA_MAX_POLICY_OPS; ++j) { boxes[j].x0 = boxes[j].y0 = 0; boxes[j].x1 = (int16_t)(W / 4); boxes[j].y1 = (int16_t)(H / 4); }
-    const int nw = std::min(FAA_MAX_FUSED_OPS, p->n_op - op_base);
-    for (int s = 0; s < p->n_sub; ++s)
-        for (int g = 0; g < (1 << nw); ++g) {
-            double pr = 1.0;
-            for (int j = 0; j < nw; ++j) {
-                double q = p->probs[(size_t)s * p->n_op + op_base + j];
-                q = q < 0 ? 0 : q > 1 ? 1 : q;
-                pr *= ((g >> j) & 1) ? q : 1.0 - q;
-            }
-            if (pr <= 0.0) continue;
-            Sample smp; memset(&smp, 0, sizeof smp);
-            smp.sub = (uint16_t)s; smp.gate = (uint8_t)(g << op_base);
-            Prog prog;
-            build_prog(smp, boxes, flat.data(), p->n_op, op_base, apply_tail, H, W, out_w, allow, prog);
-            const double w = pr * (double)prog_cost(prog);
-            total += w;
-            if (!prog_is_light(prog)) heavy += w;
-        }
-    return total > 0.0 ? heavy / total : 0.0;
 }
 
 // ------------------------------------------------------------ device tables --
@@ -685,22 +648,6 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     }
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
-    if (use_split) {
-        // the cluster kernel gets its expected share of the CTA slots, the light kernel runs next to it
-        static int sm_count = 0;
-        if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-        const int max_cl = std::max(1, sm_count * 4 / P.bands);
-        std::lock_guard<std::mutex> lk(p->mu);
-        const std::array<int, 8> hk = {h, w, tail->out_w, (int)R.allow, op_base, apply_tail, 0, 0};
-        auto it = p->share_cache.find(hk);
-        if (it == p->share_cache.end())
-            it = p->share_cache.emplace(hk, heavy_share(p, host_table_nolock(p, h, w), h, w, tail->out_w, R.allow, op_base, apply_tail)).first;
-        const double share = it->second;
-        static const double force = [] { const char* e = getenv("FAA_HEAVY_SHARE"); return e ? atof(e) : -1.0; }();
-        const double sh = force >= 0.0 ? force : (share > 0.85 ? 1.0 : share);
-        int hc = (int)(sh * max_cl + 0.5);
-        P.heavy_clusters = hc < 1 ? 1 : hc > max_cl ? max_cl : hc;
-    }
     // resolve-ahead: did the previous call already resolve exactly this batch on the side stream?
     const bool spec_ok = allow_ahead && !ahead_off && rng && !d_samples && !d_partner;
     faa_policy::AheadKey key; memset(&key, 0, sizeof key);

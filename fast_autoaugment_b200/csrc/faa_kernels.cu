@@ -122,11 +122,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
 // TMA 1-D bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
-}
-__device__ __forceinline__ void tma_issue(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+__device__ __forceinline__ void tma_stage(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
     const uint32_t b = smem_u32(bar), d = smem_u32(dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
@@ -776,22 +775,9 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     // schedule and the programs it writes are only read after this point.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule and is
-    // launched with a LIMITED number of clusters (its share of the SMs' CTA slots, so that the light
-    // streaming kernel runs next to it); each cluster walks its entries with stride gridDim.y
-    const int n_mine = P.n_heavy != nullptr ? *P.n_heavy : P.B;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < NSRC; ++s) mbar_init(&s_bar[s]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
-    const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
-    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
-    uint32_t phase = 0;
-  for (int slot = blockIdx.y; slot < n_mine; slot += gridDim.y, phase ^= 1u) {        // cluster-uniform
-    __syncthreads();                 // previous image's band, state and s_img are free
-    if (threadIdx.x == 0) s_img = P.order ? P.order[P.first + slot] : slot;                // LPT schedule
+    // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule
+    if (P.n_heavy != nullptr && (int)blockIdx.y >= *P.n_heavy) return;      // cluster-uniform
+    if (threadIdx.x == 0) s_img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
     __syncthreads();
     const int img = s_img;
     int src_idx[NSRC];
@@ -802,7 +788,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     if (threadIdx.x == 0 && s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s)
-            tma_issue(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
+            tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
     }
     // per-image programs -> shared memory (24 words each)
 #pragma unroll
@@ -813,9 +799,12 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     __syncthreads();
     if (s_len) {
 #pragma unroll
-        for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], phase);
+        for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
     }
 
+    const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
+    const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
+    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
     const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
     bool any_stats = false;
@@ -850,8 +839,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
         final_pass_mix<OUT, TAB>(P, s_norm, st, c0, c1, out_img, band);
     }
 
-    (void)any_stats;   // statistics exchanges end with their own cluster barrier (exchange_stats)
-  }
+    (void)any_stats;   // statistics exchanges end with their own cluster barrier (build_slot_lut)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -879,11 +867,7 @@ __global__ void __launch_bounds__(kThreads, 5) faa_augment_light_kernel(const __
     __syncthreads();
     const int img = s_img;
     const int idx = P.first + img;
-    if (threadIdx.x == 0 && s_len) {
-        mbar_init(&s_bar);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tma_issue(&s_bar, s_dyn, P.in + (size_t)idx * img_bytes + s_lo, s_len);
-    }
+    if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)idx * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
         reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
     __syncthreads();
@@ -988,8 +972,7 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
         configured = dyn;
     }
     cudaLaunchConfig_t cfg = {};
-    const int n_cl = (p.n_heavy != nullptr && p.heavy_clusters > 0 && p.heavy_clusters < p.B) ? p.heavy_clusters : p.B;
-    cfg.gridDim = dim3((unsigned)p.bands, (unsigned)n_cl, 1);
+    cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;

@@ -57,7 +57,6 @@ struct AugParams {
     int32_t crop_pad;           // max |crop_dy| (RandomCrop padding)
     int32_t mat_cap;            // bytes of the materialisation chunk (0: none), a whole number of rows >= 3
     int32_t pdl;                // launched with programmatic stream serialization
-    int32_t heavy_clusters;     // split launches: clusters of the cluster kernel (its share of the CTA slots)
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };
