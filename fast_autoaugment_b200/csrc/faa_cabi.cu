@@ -623,7 +623,9 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     static const bool split_off = [] { const char* e = getenv("FAA_SPLIT"); return e && e[0] == '0'; }();
     static const bool ahead_off = [] { const char* e = getenv("FAA_AHEAD"); return e && e[0] == '0'; }();
     const bool use_order = !(d_partner || lpt_off);
-    const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC;
+    // (small launches are launch-latency bound: one pixel kernel is faster there)
+    const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC &&
+                           (size_t)batch * h * w >= ((size_t)4 << 20);
     R.split = use_split ? 1 : 0;
     // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[cap]
     const size_t cap_imgs = p->d_progs_bytes / sizeof(Prog);

@@ -108,7 +108,9 @@ int         faa_op_range(int op_id, double* low, double* high);   /* augmentatio
 
 /* ---- policy: replaces Augmentation.__init__ (data.py:254-255) over the archive.py
  *      list-of-sub-policies format.  ops/probs/levels are row-major [n_sub][n_op].
- *      Magnitudes are range-checked here (the reference asserts per call).        */
+ *      Like the reference, an unknown op / out-of-range magnitude is only an error when the op
+ *      is actually applied: the host sampler reports it then (KeyError / AssertionError); the
+ *      device sampler, which cannot raise, refuses such a policy up front.            */
 int faa_policy_create(const int32_t* op_ids, const double* probs, const double* levels,
                       int n_sub, int n_op, faa_policy_t** out);
 int faa_policy_destroy(faa_policy_t* p);
