@@ -675,8 +675,16 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     p->ahead_valid = false;
     if (P.n_heavy || spec_ok) {
         if (!p->light_stream) {
-            CK(cudaStreamCreateWithFlags(&p->light_stream, cudaStreamNonBlocking));
-            CK(cudaStreamCreateWithFlags(&p->ahead_stream, cudaStreamNonBlocking));
+            {
+                int lo = 0, hi = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // hi = numerically lowest = greatest priority
+                CK(cudaStreamCreateWithPriority(&p->light_stream, cudaStreamNonBlocking, hi));
+            }
+            {
+                int lo = 0, hi = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CK(cudaStreamCreateWithPriority(&p->ahead_stream, cudaStreamNonBlocking, hi));   // one block: get a slot promptly
+            }
             CK(cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&p->ev_light, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&p->ev_ahead, cudaEventDisableTiming));
@@ -703,11 +711,22 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     }
     // launch 2: pixels
     if (P.n_heavy) {
-        // the light streaming kernel runs CONCURRENTLY with the cluster kernel on a side stream
-        CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
-        CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
-        CK(launch_augment(P, tail->out_dtype, use_tab, true, p->light_stream));
-        CK(cudaEventRecord(p->ev_light, p->light_stream));
+        // Two pixel kernels, concurrently: the light streaming kernel goes first on the caller's
+        // stream and fills the machine; the cluster kernel runs on a HIGH-PRIORITY side stream, so its
+        // clusters take the CTA slots as they free up (heavy images finish early, light work fills gaps).
+        static const bool prio_off = [] { const char* e = getenv("FAA_PRIO"); return e && e[0] == '0'; }();
+        if (prio_off) {
+            CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
+            CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
+            CK(launch_augment(P, tail->out_dtype, use_tab, true, p->light_stream));
+            CK(cudaEventRecord(p->ev_light, p->light_stream));
+        } else {
+            AugParams Ph = P; Ph.pdl = 0;                           // not behind the resolve kernel in its stream
+            CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
+            CK(launch_augment(P, tail->out_dtype, use_tab, true, stream));
+            CK(launch_augment(Ph, tail->out_dtype, use_tab, false, p->light_stream));
+            CK(cudaEventRecord(p->ev_light, p->light_stream));
+        }
         CK(cudaStreamWaitEvent(stream, p->ev_light, 0));
         g_launches += 2;
     } else {
