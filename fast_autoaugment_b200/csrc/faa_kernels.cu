@@ -413,38 +413,69 @@ __device__ __forceinline__ uint32_t load_raw_cg(const Ctx& c, int x, int y) {   
     // so they are coherent with the peers' stores and still L1-cached for the gather's locality
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
 }
-template <bool COH>
-__device__ __forceinline__ void quad_geom(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
-    const int g = (c.op[0].kind == K_AFFINE || c.op[0].kind == K_SHIFT) ? 0 : 1;
-    const OpRec& o = c.op[g];
-    const int ay = oy + t.crop_dy;
-    const int ax0 = (t.flip ? (out_w - 1 - ox0) : ox0) + t.crop_dx;
+// The geometric op of a C_GEOM / C_SG program as plain registers (no indexed access to the op array).
+struct GeomOp {
+    int a0, a1, a2, a3, a4, a5;   // K_AFFINE: 16.16 coefficients; K_SHIFT: a0=dx a1=dy a2=bx a3=by
+    int pk;                       // kind of the pointwise op in the other slot (K_NONE: nothing)
+};
+
+// G = slot of the geometric op, AFF = it is a K_AFFINE (else K_SHIFT), SIMPLE = the tail is the identity
+// apart from the flip (no crop, out size == image size, out_w % 4 == 0): every pixel of the quad exists
+template <int G, bool AFF, bool SIMPLE, bool COH>
+__device__ __forceinline__ void quad_geom(const Ctx& c, const GeomOp& o, const TailInfo& t, int out_w, int ox0, int oy,
+                                          uint32_t px[4]) {
+    const int ay = SIMPLE ? oy : oy + t.crop_dy;
+    const int ax0 = (t.flip ? (out_w - 1 - ox0) : ox0) + (SIMPLE ? 0 : t.crop_dx);
     const int sx = t.flip ? -1 : 1;
-    const bool row_ok = (unsigned)ay < (unsigned)c.H;
-    int fx, fy, dfx, dfy;                              // 16.16 source coordinates of pixel k = 0 and their step
-    if (o.kind == K_AFFINE) {
-        fx = o.a[2] + o.a[0] * ax0 + o.a[1] * ay; fy = o.a[5] + o.a[3] * ax0 + o.a[4] * ay;
-        dfx = sx * o.a[0]; dfy = sx * o.a[3];
-    } else { fx = fy = dfx = dfy = 0; }
+    const bool row_ok = SIMPLE || (unsigned)ay < (unsigned)c.H;
+    int fx = 0, fy = 0, dfx = 0, dfy = 0;               // 16.16 source coordinates of pixel k = 0 and their step
+    if (AFF) {
+        fx = o.a2 + o.a0 * ax0 + o.a1 * ay; fy = o.a5 + o.a3 * ax0 + o.a4 * ay;
+        dfx = sx * o.a0; dfy = sx * o.a3;
+    }
+    const int ysh = AFF ? 0 : ay + o.a1 + (ay >= o.a3);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int ax = ax0 + sx * k;
         uint32_t p = 0u;
-        bool have = false;
-        int xs = 0, ys = 0;
-        if (row_ok && (unsigned)ax < (unsigned)c.W && ox0 + k < out_w) {
-            have = true;                                // (ax, ay) is a pixel of the augmented image
-            if (o.kind == K_AFFINE) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
-            else { xs = ax + o.a[0] + (ax >= o.a[2]); ys = ay + o.a[1] + (ay >= o.a[3]); }
-            const bool inside = (unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H;
-            if (inside) {
+        const bool have = SIMPLE || (row_ok && (unsigned)ax < (unsigned)c.W && ox0 + k < out_w);
+        if (have) {                                      // (ax, ay) is a pixel of the augmented image
+            int xs, ys;
+            if (AFF) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
+            else { xs = ax + o.a0 + (ax >= o.a2); ys = ysh; }
+            if ((unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H) {
                 p = COH ? load_raw_cg(c, xs, ys) : load_raw(c, xs, ys);
-                if (g == 1) p = apply_pointwise(c, 0, p, xs, ys);        // op0 ran before the gather
+                if (G == 1 && o.pk != K_NONE) p = apply_pointwise(c, 0, p, xs, ys);     // op0 ran before the gather
             }
-            if (g == 0) p = apply_pointwise(c, 1, p, ax, ay);            // op1 runs after it (fill included)
+            if (G == 0 && o.pk != K_NONE) p = apply_pointwise(c, 1, p, ax, ay);         // op1 runs after it (fill included)
         }
-        px[k] = have ? p : 0u;
+        px[k] = p;
     }
+}
+
+// runtime -> compile-time dispatch of the variants (CTA-uniform), one call per quad
+template <bool COH>
+__device__ __forceinline__ void quad_geom_any(int variant, const Ctx& c, const GeomOp& o, const TailInfo& t, int out_w,
+                                              int ox0, int oy, uint32_t px[4]) {
+    switch (variant) {
+    case 0: quad_geom<0, false, false, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 1: quad_geom<0, false, true, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 2: quad_geom<0, true, false, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 3: quad_geom<0, true, true, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 4: quad_geom<1, false, false, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 5: quad_geom<1, false, true, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 6: quad_geom<1, true, false, COH>(c, o, t, out_w, ox0, oy, px); break;
+    default: quad_geom<1, true, true, COH>(c, o, t, out_w, ox0, oy, px); break;
+    }
+}
+
+__device__ __forceinline__ int geom_setup(const Ctx& c, const TailInfo& t, int H, int W, int out_h, int out_w, GeomOp& o) {
+    const bool g0 = c.op[0].kind == K_AFFINE || c.op[0].kind == K_SHIFT;
+    const OpRec& r = g0 ? c.op[0] : c.op[1];
+    o.a0 = r.a[0]; o.a1 = r.a[1]; o.a2 = r.a[2]; o.a3 = r.a[3]; o.a4 = r.a[4]; o.a5 = r.a[5];
+    o.pk = g0 ? c.op[1].kind : c.op[0].kind;
+    const bool simple = t.crop_dx == 0 && t.crop_dy == 0 && out_h == H && out_w == W && (out_w & 3) == 0;
+    return (g0 ? 0 : 4) + (r.kind == K_AFFINE ? 2 : 0) + (simple ? 1 : 0);
 }
 
 __device__ __forceinline__ void quad_generic(const Ctx& c, const TailInfo& t, int out_w, int ox0, int oy, uint32_t px[4]) {
@@ -540,13 +571,15 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
     // incremental (row, quad) walk: one division up front, adds afterwards
     uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
     const uint32_t dr = dq.div(blockDim.x), dx = blockDim.x - dr * qpr;
+    GeomOp go; int gv = 0;
+    if (CLS == C_GEOM || CLS == C_SG) gv = geom_setup(c, t, P.H, P.W, P.out_h, P.out_w, go);
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
         const int ox0 = (int)qx * 4;
         const int oy = oy0 + (int)r;
         uint32_t px[4];
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
-        else if (CLS == C_GEOM) quad_geom<false>(c, t, P.out_w, ox0, oy, px);
-        else if (CLS == C_SG) quad_geom<true>(c, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_GEOM) quad_geom_any<false>(gv, c, go, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_SG) quad_geom_any<true>(gv, c, go, t, P.out_w, ox0, oy, px);
         else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
         qx += dx; r += dr;
@@ -583,6 +616,8 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
         const uint32_t qpr = (uint32_t)W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
         FastDiv dq; dq.init(qpr, c.rcp_wq);
         TailInfo id; id.crop_dy = id.crop_dx = id.flip = 0; id.zb0 = id.zb1 = id.zb2 = id.zb3 = 0;
+        GeomOp go; int gv = 0;
+        if (cls0 == C_GEOM) gv = geom_setup(c, id, c.H, W, c.H, W, go);
         for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
             const uint32_t r = dq.div(q);
             const int x0 = (int)(q - r * qpr) * 4, y = r0 + (int)r;
@@ -591,7 +626,7 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
             case C_LUT:   quad_vec<C_LUT>(c, lut0, id, W, x0, y, p); break;
             case C_POINT: quad_vec<C_POINT>(c, lut0, id, W, x0, y, p); break;
             case C_SHARP: quad_vec<C_SHARP>(c, lut0, id, W, x0, y, p); break;
-            case C_GEOM:  quad_geom<false>(c, id, W, x0, y, p); break;
+            case C_GEOM:  quad_geom_any<false>(gv, c, go, id, W, x0, y, p); break;
             default:
 #pragma unroll
                 for (int k = 0; k < 4; ++k) p[k] = Level<1>::at(c, x0 + k, y);
