@@ -369,11 +369,40 @@ __device__ __forceinline__ uint32_t zero_mask(const TailInfo& t, int ox0, int oy
     return m;
 }
 
+// one pointwise op with its kind known at compile time (PK: 0 none, 1 LUT, 2 Color, 3 Cutout)
+template <int PK>
+__device__ __forceinline__ uint32_t point_op(const Ctx& c, int j, uint32_t p, int x, int y) {
+    if (PK == 1) return apply_lut(c.lut[j], p);
+    if (PK == 2) return color_px(p, bits_to_float(c.op[j].a[0]), c.op[j].a[1] != 0);
+    if (PK == 3) { const Box& b = c.box[j]; return (x >= b.x0 && x <= b.x1 && y >= b.y0 && y <= b.y1) ? kCutoutRGB : p; }
+    return p;
+}
+__device__ __forceinline__ int point_kind(int k) { return k == K_NONE ? 0 : k == K_COLOR ? 2 : k == K_CUTOUT ? 3 : 1; }
+
+template <int PK0, int PK1>
+__device__ __forceinline__ void point4(const Ctx& c, uint32_t q[4], int sx0, int ay) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = point_op<PK1>(c, 1, point_op<PK0>(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+}
+// CTA-uniform dispatch on the two slots' pointwise kinds (pv = 4 * kind0 + kind1)
+__device__ __forceinline__ void point4_any(int pv, const Ctx& c, uint32_t q[4], int sx0, int ay) {
+    switch (pv) {
+    case 1: point4<0, 1>(c, q, sx0, ay); break;   case 2: point4<0, 2>(c, q, sx0, ay); break;
+    case 3: point4<0, 3>(c, q, sx0, ay); break;   case 4: point4<1, 0>(c, q, sx0, ay); break;
+    case 5: point4<1, 1>(c, q, sx0, ay); break;   case 6: point4<1, 2>(c, q, sx0, ay); break;
+    case 7: point4<1, 3>(c, q, sx0, ay); break;   case 8: point4<2, 0>(c, q, sx0, ay); break;
+    case 9: point4<2, 1>(c, q, sx0, ay); break;   case 10: point4<2, 2>(c, q, sx0, ay); break;
+    case 11: point4<2, 3>(c, q, sx0, ay); break;  case 12: point4<3, 0>(c, q, sx0, ay); break;
+    case 13: point4<3, 1>(c, q, sx0, ay); break;  case 14: point4<3, 2>(c, q, sx0, ay); break;
+    case 15: point4<3, 3>(c, q, sx0, ay); break;  default: break;
+    }
+}
+
 // aligned classes: the four source pixels of an output quad are 12 contiguous bytes.
 // `slot` is the op slot a C_SHARP program's Sharpness sits in (0) / its pointwise follower (1).
 template <int CLS>
 __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, const TailInfo& t, int out_w, int ox0,
-                                         int oy, uint32_t px[4]) {
+                                         int oy, uint32_t px[4], int pv = 0) {
     const int sx0 = (t.flip ? (out_w - 4 - ox0) : ox0) + t.crop_dx;
     const int ay = oy + t.crop_dy;
     uint32_t q[4] = {0u, 0u, 0u, 0u};
@@ -395,9 +424,7 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k) q[k] = apply_lut(lutc, q[k]);
             } else if (CLS == C_POINT) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    q[k] = apply_pointwise(c, 1, apply_pointwise(c, 0, q[k], sx0 + k, ay), sx0 + k, ay);
+                point4_any(pv, c, q, sx0, ay);
             }
         }
     }
@@ -573,6 +600,7 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
     const uint32_t dr = dq.div(blockDim.x), dx = blockDim.x - dr * qpr;
     GeomOp go; int gv = 0;
     if (CLS == C_GEOM || CLS == C_SG) gv = geom_setup(c, t, P.H, P.W, P.out_h, P.out_w, go);
+    if (CLS == C_POINT) gv = 4 * point_kind(c.op[0].kind) + point_kind(c.op[1].kind);
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
         const int ox0 = (int)qx * 4;
         const int oy = oy0 + (int)r;
@@ -580,7 +608,7 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
         else if (CLS == C_GEOM) quad_geom_any<false>(gv, c, go, t, P.out_w, ox0, oy, px);
         else if (CLS == C_SG) quad_geom_any<true>(gv, c, go, t, P.out_w, ox0, oy, px);
-        else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px);
+        else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px, gv);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
         qx += dx; r += dr;
         if (qx >= qpr) { qx -= qpr; ++r; }
@@ -624,7 +652,7 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
             uint32_t p[4];
             switch (cls0) {
             case C_LUT:   quad_vec<C_LUT>(c, lut0, id, W, x0, y, p); break;
-            case C_POINT: quad_vec<C_POINT>(c, lut0, id, W, x0, y, p); break;
+            case C_POINT: quad_vec<C_POINT>(c, lut0, id, W, x0, y, p, 4 * point_kind(c.op[0].kind) + point_kind(c.op[1].kind)); break;
             case C_SHARP: quad_vec<C_SHARP>(c, lut0, id, W, x0, y, p); break;
             case C_GEOM:  quad_geom_any<false>(gv, c, go, id, W, x0, y, p); break;
             default:
@@ -767,11 +795,11 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
         if (cls0 == C_GENERIC || cls0 == C_GEOM || cls0 == C_SG) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_LUT) quad_vec<C_LUT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_SHARP) quad_vec<C_SHARP>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
-        else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
+        else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa, 4 * point_kind(c0.op[0].kind) + point_kind(c0.op[1].kind));
         if (cls1 == C_GENERIC || cls1 == C_GEOM || cls1 == C_SG) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_LUT) quad_vec<C_LUT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_SHARP) quad_vec<C_SHARP>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
-        else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
+        else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb, 4 * point_kind(c1.op[0].kind) + point_kind(c1.op[1].kind));
         const uint32_t za = zero_mask(t0, ox0, oy), zb = zero_mask(t1, ox0, oy);
         const int nvalid = min(4, P.out_w - ox0);
         T* o = reinterpret_cast<T*>(out_img) + (uint32_t)(oy * P.out_w + ox0);
