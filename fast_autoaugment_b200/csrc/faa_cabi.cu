@@ -541,6 +541,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
                           float lam, float oml, int apply_tail, bool allow_ahead, void* stream_v) {
     if (!p || (!d_in_all && batch > 0) || (!d_out && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
     if (batch < 0 || first < 0 || first + batch > n_all) return fail(FAA_ERR_VALUE, "bad batch range");
+    if (batch > 65535) return fail(FAA_ERR_UNSUPPORTED, "at most 65535 images per call (one grid row per image): split the batch");
     if (int e = check_shape(h, w)) return e;
     if (int e = check_tail(tail)) return e;
     if (!d_samples && !rng) return fail(FAA_ERR_VALUE, "need either resolved samples or an rng config");

@@ -10,9 +10,10 @@
 // Geometric ops remap the coordinate, per-channel ops go through a 3x256 byte LUT built
 // once per image (static LUTs, AutoContrast/Equalize from the histogram, Brightness /
 // Contrast blends), Color and Cutout are evaluated in registers, Sharpness evaluates its
-// 3x3 neighbourhood one level down.  No intermediate image is ever materialised, so the
-// whole chain needs no second image buffer and no barrier between ops; only the ops that
-// need whole-image statistics (AutoContrast, Equalize, Contrast) cost one extra pass.
+// 3x3 neighbourhood one level down.  The chain needs no second image buffer in global memory
+// and no barrier between ops; the kernels only materialise an intermediate image (in shared
+// memory) where lazy evaluation would repeat work (Sharpness or a statistics op behind another
+// op), and the ops that need whole-image statistics cost one extra pass over the row band.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>

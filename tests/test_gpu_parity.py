@@ -327,3 +327,59 @@ def test_translate_accumulator_break():
     samples, boxes = pol.sample_parity(len(batch), 380, 380)
     got = augment_batch(pol, dev(batch), TailSpec.raw_u8(), samples, boxes).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+def test_resolve_ahead_and_split_paths_are_invisible():
+    """fused Philox launches at a size that takes the split (light + cluster kernel) path, called
+    back to back so that the resolve-ahead speculation hits, with a stride change and a seed change
+    in the sequence: every result must equal the one computed from the device sampler's records"""
+    import ctypes as C
+    from fast_autoaugment_b200.engine import FusedAugmenter
+    policies = archive.fa_resnet50_rimagenet()
+    tail = TailSpec.imagenet(0, torch.float16)
+    B, H, W = 96, 224, 224
+    x = dev(synth_batch(B, (H, W), seed=21))
+    pol = CompiledPolicy(policies)
+    f = FusedAugmenter(pol, tail, H, W, seed=5)
+    t = tail.c_struct(H, W)
+    firsts = [0, B, 2 * B, 3 * B, 10 * B, 17 * B, 24 * B, 24 * B, 7]          # hits, stride change, repeat, odd
+    outs = []
+    for fi in firsts:
+        outs.append(f(x, f.empty_out(B), fi).clone())
+    f.rng.seed = 6
+    outs.append(f(x, f.empty_out(B), 8 * B).clone())
+    firsts.append(8 * B)
+    torch.cuda.synchronize()
+    ref_pol = CompiledPolicy(policies)                                           # fresh handle: no speculation state
+    for k, fi in enumerate(firsts):
+        rng = make_rng(6 if k == len(firsts) - 1 else 5, fi, tail)
+        d_s = torch.zeros(B * 16, dtype=torch.uint8, device="cuda")
+        d_b = torch.zeros(B * 2 * 8, dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.lib.faa_sample_philox(ref_pol.handle, B, H, W, C.byref(t), C.byref(rng), d_s.data_ptr(),
+                                              d_b.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        want = augment_batch(ref_pol, x, tail, d_s, d_b)
+        assert torch.equal(outs[k], want), (k, fi)
+
+
+@pytest.mark.parametrize("shape,n", [((160, 160), 48), ((8, 2048), 24), ((1, 4), 5), ((4, 4), 1)])
+def test_odd_geometries(shape, n):
+    """4-band clusters (160x160), rows too wide for the materialisation chunk (lazy fallback),
+    degenerate images, batch of 1"""
+    rng = random.Random(shape[0])
+    names = ["Rotate", "Equalize", "Sharpness", "Contrast", "ShearY", "Color", "AutoContrast", "TranslateY", "Cutout"]
+    policies = [[(rng.choice(names), 1.0, rng.random()), (rng.choice(names), 1.0, rng.random())] for _ in range(60)]
+    pol = CompiledPolicy(policies)
+    batch = synth_batch(n, shape, seed=shape[1])
+    seed_all(4)
+    want = oracle_policy(policies, batch)
+    seed_all(4)
+    samples, boxes = pol.sample_parity(n, shape[0], shape[1])
+    got = augment_batch(pol, dev(batch), TailSpec.raw_u8(), samples, boxes).cpu().numpy()
+    bad = [i for i in range(n) if not np.array_equal(got[i], want[i])]
+    assert not bad, (shape, bad[:5], [policies[samples[i]["sub"]] for i in bad[:5]])
+    tail = TailSpec(None, 0, True, IMAGENET_MEAN, IMAGENET_STD, 0, torch.float32)
+    seed_all(4)
+    want_f = pil_path.run_chain_on_batch(pil_path.fixed_shape_chain(policies, IMAGENET_MEAN, IMAGENET_STD, True, 0), batch)
+    seed_all(4)
+    samples, boxes = pol.sample_parity(n, shape[0], shape[1], tail)
+    assert torch.equal(augment_batch(pol, dev(batch), tail, samples, boxes).cpu(), want_f)
