@@ -43,7 +43,7 @@ class Augmentation(object):
         arr = np.ascontiguousarray(np.asarray(img.convert("RGB")))
         h, w = arr.shape[:2]
         samples, boxes = self.compiled.sample_parity(1, h, w, TailSpec.raw_u8())
-        y = augment_batch(self.compiled, torch.from_numpy(arr[None]).cuda(), TailSpec.raw_u8(), samples, boxes)
+        y = augment_batch(self.compiled, torch.from_numpy(arr[None].copy()).cuda(), TailSpec.raw_u8(), samples, boxes)
         return PIL.Image.fromarray(y[0].cpu().numpy())
 
     def augment_batch(self, batch_u8, tail: TailSpec | None = None, seed=None, first_index=0, parity=False,
