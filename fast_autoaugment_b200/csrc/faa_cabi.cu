@@ -651,17 +651,6 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     }
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
-    // small single-band launches are launch-latency bound: fold the resolve step into the pixel kernel
-    static const bool inline_off = [] { const char* e = getenv("FAA_INLINE"); return e && e[0] == '0'; }();
-    if (!inline_off && P.bands == 1 && rng && !d_samples && !d_partner && p->n_op <= FAA_MAX_FUSED_OPS && apply_tail &&
-        (size_t)batch * h * w < ((size_t)4 << 20)) {
-        P.inline_resolve = 1; P.ops = d_ops; P.probs = p->d_probs; memcpy(&P.rng, rng, sizeof(RngCfg));
-        P.n_sub = p->n_sub; P.n_op = p->n_op; P.allow = R.allow; P.pdl = 0;
-        P.progs = nullptr; P.order = nullptr; P.n_heavy = nullptr;
-        CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
-        g_launches++;
-        return FAA_OK;
-    }
     // resolve-ahead: did the previous call already resolve exactly this batch on the side stream?
     const bool spec_ok = allow_ahead && !ahead_off && rng && !d_samples && !d_partner;
     faa_policy::AheadKey key; memset(&key, 0, sizeof key);

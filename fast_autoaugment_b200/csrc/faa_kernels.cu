@@ -819,7 +819,7 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
 
 // ---------------------------------------------------------------------------------------
 // launch 2
-template <int OUT, int NSRC, bool TAB, bool INLINE>
+template <int OUT, int NSRC, bool TAB>
 __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
     extern __shared__ __align__(128) uint8_t s_dyn[];           // NSRC staged row bands [+ materialisation chunk]
     cg::cluster_group cluster = cg::this_cluster();
@@ -853,22 +853,12 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
         for (int s = 0; s < NSRC; ++s)
             tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
     }
-    if constexpr (INLINE) {
-        // small single-band launches: no separate resolve launch, thread 0 draws the decisions here
-        if (threadIdx.x == 0) {
-            Sample smp; Box bx[8];
-            philox_sample(P.rng, P.rng.first_index + (uint64_t)src_idx[0], P.ops, P.probs, P.n_sub, P.n_op, P.H, P.W,
-                          P.out_h, P.out_w, smp, bx);
-            build_prog(smp, bx, P.ops, P.n_op, 0, 1, P.H, P.W, P.out_w, P.allow, st[0].prog);
-        }
-    } else {
-        // per-image programs -> shared memory (24 words each)
+    // per-image programs -> shared memory (24 words each)
 #pragma unroll
-        for (int s = 0; s < NSRC; ++s)
-            if (threadIdx.x < sizeof(Prog) / 4)
-                reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
-                    __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
-    }
+    for (int s = 0; s < NSRC; ++s)
+        if (threadIdx.x < sizeof(Prog) / 4)
+            reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
+                __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
     __syncthreads();
     if (s_len) {
 #pragma unroll
@@ -1034,12 +1024,12 @@ uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
     return (cap + 127u) & ~127u;
 }
 
-template <int OUT, int NSRC, bool TAB, bool INLINE = false>
+template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     const size_t dyn = (size_t)p.geo[0].band_cap * NSRC + (size_t)p.mat_cap;
     static size_t configured = 0;                   // per instantiation
     if (dyn > configured) {
-        cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB, INLINE>,
+        cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
         configured = dyn;
@@ -1058,7 +1048,7 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = p.pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB, INLINE>, p);
+    return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
 
 template <int OUT, bool TAB>
@@ -1079,7 +1069,6 @@ template <int OUT>
 static cudaError_t launch_out(const AugParams& p, bool mix, bool tab, bool light, cudaStream_t stream) {
     if (light) return tab ? launch_light<OUT, true>(p, stream) : launch_light<OUT, false>(p, stream);
     if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
-    if (p.inline_resolve) return tab ? launch_one<OUT, 1, true, true>(p, stream) : launch_one<OUT, 1, false, true>(p, stream);
     return tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
 }
 

@@ -59,10 +59,6 @@ struct AugParams {
     int32_t pdl;                // launched with programmatic stream serialization
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
-    // inline resolve (small single-band launches: one launch instead of two): the CTA draws its image's
-    // decisions itself, exactly like faa_resolve_kernel would
-    const OpRec* ops; const double* probs; RngCfg rng;
-    int32_t n_sub, n_op, inline_resolve, allow;
 };
 cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, bool light, cudaStream_t stream);
 
