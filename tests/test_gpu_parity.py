@@ -383,3 +383,39 @@ def test_odd_geometries(shape, n):
     seed_all(4)
     samples, boxes = pol.sample_parity(n, shape[0], shape[1], tail)
     assert torch.equal(augment_batch(pol, dev(batch), tail, samples, boxes).cpu(), want_f)
+
+
+def test_device_resident_loader_matches_oracle_chain():
+    """get_dataloaders counterpart (reference data.py:37-225, row N1): device-resident uint8 dataset,
+    batches come out augmented on the GPU; in parity mode they equal the reference chain applied to
+    the same samples in the same order"""
+    from fast_autoaugment_b200.data import GpuAugmentedLoader, get_dataloaders
+    n, b = 96, 32
+    images = synth_batch(n, (32, 32), seed=50)
+    labels = np.arange(n) % 10
+    policies = archive.fa_reduced_cifar10()
+    tail = TailSpec.cifar(16, torch.float32)
+    loader = GpuAugmentedLoader(images, labels, b, policies, tail, shuffle=False, parity=True)
+    assert len(loader) == 3
+    seed_all(13)
+    got = [(d.cpu(), l.cpu()) for d, l in loader]
+    seed_all(13)
+    want = pil_path.run_chain_on_batch(pil_path.cifar_train_chain(policies, 16), images)
+    assert torch.equal(torch.cat([d for d, _ in got]), want)
+    assert torch.equal(torch.cat([l for _, l in got]), torch.from_numpy(labels))
+    # fused-Philox loaders: deterministic per (seed, epoch), reshuffled by set_epoch, CUDA fp16 NCHW out
+    sampler, train, valid, test = get_dataloaders("cifar10", b, images, labels, aug="fa_reduced_cifar10", cutout=16,
+                                                  test_images=images[:b], test_labels=labels[:b])
+    a = [d.clone() for d, _ in train]
+    bb = [d.clone() for d, _ in train]
+    assert all(torch.equal(x, y) for x, y in zip(a, bb))
+    assert a[0].is_cuda and a[0].dtype == torch.float16 and tuple(a[0].shape) == (b, 3, 32, 32)
+    sampler.set_epoch(1)
+    c = [d.clone() for d, _ in train]
+    assert not torch.equal(a[0], c[0])
+    t0 = next(iter(test))[0]
+    ref = torch.from_numpy(np.stack([pil_path.fixed_shape_chain(None, pil_path.CIFAR_MEAN, pil_path.CIFAR_STD, False, 0)(
+        PIL.Image.fromarray(im)).numpy() for im in images[:b]]))
+    assert torch.equal(t0.cpu(), ref.half())
+    with pytest.raises(ValueError):
+        get_dataloaders("mnist", b, images, labels)
