@@ -49,7 +49,7 @@ def _run_single(img, policy_list):
     pol = CompiledPolicy(policy_list)
     h, w = arr.shape[:2]
     samples, boxes = pol.sample_parity(1, h, w, TailSpec.raw_u8())
-    x = torch.from_numpy(np.ascontiguousarray(arr)[None]).cuda()
+    x = torch.from_numpy(np.ascontiguousarray(arr)[None].copy()).cuda()
     y = augment_batch(pol, x, TailSpec.raw_u8(), samples, boxes)
     return PIL.Image.fromarray(y[0].cpu().numpy())
 
