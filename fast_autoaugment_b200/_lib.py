@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfaa_b200.so")
+LIB_PATH = os.environ.get("FAA_B200_LIB") or os.path.join(_HERE, "libfaa_b200.so")   # env: tuning builds only
 
 # ---- status codes (enum faa_status) and the reference exceptions they stand for
 OK, ERR_UNKNOWN_OP, ERR_MAGNITUDE, ERR_VALUE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(7)

@@ -909,8 +909,11 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
 // launch 3: the streaming kernel for "light" images (no statistics, no neighbourhood ops):
 // PLAIN / LUT / POINT / GEOM classes only - no cluster, 3 KB of static shared memory, a fraction of
 // the cluster kernel's registers and code.  It owns schedule entries [n_heavy, B).
+#ifndef FAA_LIGHT_CTAS
+#define FAA_LIGHT_CTAS 5
+#endif
 template <int OUT, bool TAB>
-__global__ void __launch_bounds__(kThreads, 5) faa_augment_light_kernel(const __grid_constant__ AugParams P) {
+__global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_kernel(const __grid_constant__ AugParams P) {
     extern __shared__ __align__(128) uint8_t s_dyn[];           // staged row band
     __shared__ Prog s_prog;
     __shared__ __align__(16) uint8_t s_lut[2][768];
