@@ -253,9 +253,14 @@ __device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool want_hist,
             for (int i = threadIdx.x; i < slice; i += blockDim.x) {
                 const int bin = rank * slice + i;
                 if (bin < 768) {
-                    uint32_t t = 0;
-                    for (int r = 0; r < bands; ++r) t += cluster.map_shared_rank(&st.hist[j][0], r)[bin];
-                    for (int r = 0; r < bands; ++r) cluster.map_shared_rank(&st.tot[0], r)[bin] = t;
+                    // all remote loads in flight together (each is a ~200-cycle DSMEM round trip)
+                    uint32_t v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) v[r] = r < bands ? cluster.map_shared_rank(&st.hist[j][0], r)[bin] : 0u;
+                    const uint32_t t = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < bands) cluster.map_shared_rank(&st.tot[0], r)[bin] = t;
                 }
             }
         } else {
