@@ -596,6 +596,18 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     {   // per-kernel band geometry and fastdiv reciprocals (host side: no divisions in the kernels)
         fill_geom(P.geo[0], P.bands, h, w, tail->out_h, P.crop_pad, P.stage != 0);
         int lb = P.bands;
+        if (P.bands == 8) {
+            // the light kernel needs no cluster, so any band count works: take the one in 5..8 whose
+            // quads-per-CTA fills whole 256-thread iterations best (224x224: 7 bands = exactly 7 iterations)
+            const int qpr = (tail->out_w + 3) / 4;
+            double best = -1.0;
+            for (int b = 8; b >= 5; --b) {
+                const int rows = (tail->out_h + b - 1) / b;
+                const int quads = rows * qpr, iters = (quads + 255) / 256;
+                const double eff = (double)quads / (iters * 256.0) * ((double)tail->out_h / (rows * b));
+                if (eff > best + 0.02) { best = eff; lb = b; }
+            }
+        }
         static const int light_bands = [] { const char* e = getenv("FAA_LIGHT_BANDS"); return e ? atoi(e) : 0; }();
         if (light_bands >= 1 && light_bands <= 8 && light_bands <= h && light_bands <= tail->out_h) lb = light_bands;
         fill_geom(P.geo[1], lb, h, w, tail->out_h, P.crop_pad, P.stage != 0 && (size_t)band_capacity(lb, h, w, tail->out_h, P.crop_pad) <= 100 * 1024);
