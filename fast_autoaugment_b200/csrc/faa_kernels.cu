@@ -554,15 +554,12 @@ __device__ __forceinline__ float normalise(const AugParams& P, const float* s_no
     return fmaf((float)u, P.scale[ch], P.bias[ch]);
 }
 
-// normalise + store one quad (single source)
+// normalise + store one quad (single source); the CutoutDefault box is re-zeroed afterwards (zero_box_rows)
 template <int OUT, bool TAB>
 __device__ __forceinline__ void emit_quad(const AugParams& P, const float* s_norm, void* out_img, int ox0, int oy,
-                                          const uint32_t px_in[4], uint32_t zmask, bool vec) {
-    const int nvalid = min(4, P.out_w - ox0);
+                                          const uint32_t px[4], bool vec) {
+    const int nvalid = min(4, P.out_w - ox0);           // a static bound of 4 keeps the tail stores unrolled
     if constexpr (OUT == OUT_U8_HWC) {
-        uint32_t px[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) px[k] = ((zmask >> k) & 1u) ? 0u : px_in[k];
         uint8_t* o = reinterpret_cast<uint8_t*>(out_img) + (uint32_t)(oy * P.out_w + ox0) * 3u;
         if (vec) {
             uint32_t* w = reinterpret_cast<uint32_t*>(o);
@@ -582,11 +579,7 @@ __device__ __forceinline__ void emit_quad(const AugParams& P, const float* s_nor
         for (int ch = 0; ch < 3; ++ch) {
             float v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = normalise<TAB>(P, s_norm, ch, (px_in[k] >> (8 * ch)) & 255u);
-            if (zmask) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = ((zmask >> k) & 1u) ? 0.0f : v[k];
-            }
+            for (int k = 0; k < 4; ++k) v[k] = normalise<TAB>(P, s_norm, ch, (px[k] >> (8 * ch)) & 255u);
             store_plane4<OUT>(o + ch * plane, v, vec, nvalid);
         }
     }
@@ -599,7 +592,8 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
     const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
     FastDiv dq; dq.init(qpr, P.rcp_out_qpr);
-    const bool vec = (P.out_w & 3) == 0;
+    // aligned classes exist only when out_w % 4 == 0 (build_prog)
+    const bool vec = (CLS == C_PLAIN || CLS == C_LUT || CLS == C_POINT || CLS == C_SHARP) ? true : (P.out_w & 3) == 0;
     // incremental (row, quad) walk: one division up front, adds afterwards
     uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
     const uint32_t dr = dq.div(blockDim.x), dx = blockDim.x - dr * qpr;
@@ -614,18 +608,125 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
         else if (CLS == C_GEOM) quad_geom_any<false>(gv, c, go, t, P.out_w, ox0, oy, px);
         else if (CLS == C_SG) quad_geom_any<true>(gv, c, go, t, P.out_w, ox0, oy, px);
         else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px, gv);
-        emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, zero_mask(t, ox0, oy), vec);
+        emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, vec);
         qx += dx; r += dr;
         if (qx >= qpr) { qx -= qpr; ++r; }
     }
 }
 
+// CutoutDefault (data.py:235-250) for single-source launches: after its final pass the CTA re-zeroes its
+// rows of the image's box (zero on the normalised tensor; byte zero for the raw uint8 output)
+template <int OUT>
+__device__ __forceinline__ void zero_box_rows(const AugParams& P, const Prog& g, void* out_img, int oy0, int oy1) {
+    if (!P.use_zero_box) return;
+    const int r0 = max((int)g.zero_box[0], oy0), r1 = min((int)g.zero_box[1], oy1);
+    const int c0 = max((int)g.zero_box[2], 0), c1 = min((int)g.zero_box[3], P.out_w);
+    const int bw = c1 - c0, n = bw * (r1 - r0);
+    if (bw <= 0 || r1 <= r0) return;                    // CTA-uniform
+    __syncthreads();                                    // the final pass's stores are ordered before these
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = r0 + i / bw, x = c0 + i % bw;
+        if constexpr (OUT == OUT_U8_HWC) {
+            uint8_t* o = reinterpret_cast<uint8_t*>(out_img) + (uint32_t)(r * P.out_w + x) * 3u;
+            o[0] = 0; o[1] = 0; o[2] = 0;
+        } else {
+            using T = typename OutElem<OUT>::T;
+            const uint32_t plane = (uint32_t)P.out_h * (uint32_t)P.out_w;
+            T* o = reinterpret_cast<T*>(out_img) + (uint32_t)(r * P.out_w + x);
+            o[0] = T(0.0f); o[plane] = T(0.0f); o[2u * plane] = T(0.0f);
+        }
+    }
+}
+
+// ---- streaming loop of the PLAIN / LUT classes -------------------------------------------------
+// When every source row of the band is staged, the twelve bytes of a quad go straight from the staged
+// words to the three planes: value = tab[ch][byte] (LUT composed with the normalisation) or the fma.
+__device__ __forceinline__ bool band_fully_staged(const Ctx& c, const TailInfo& t, int oy0, int oy1) {
+    const int a0 = max(oy0 + t.crop_dy, 0), a1 = min(oy1 + t.crop_dy, c.H);        // source rows [a0, a1)
+    if (a1 <= a0) return true;
+    const uint32_t pitch = (uint32_t)c.W * 3u, s_len = c.s_len2 ? c.s_len2 + 2u : 0u;
+    return s_len != 0u && (uint32_t)a0 * pitch >= c.s_lo && (uint32_t)a1 * pitch <= c.s_lo + s_len;
+}
+
+template <int OUT, bool USE_TAB, bool FLIP>
+__device__ __forceinline__ void stream_quad(const AugParams& P, const uint32_t* w, const float* tab,
+                                            typename OutElem<OUT>::T* o, uint32_t plane) {
+    const uint32_t w3[3] = {w[0], w[1], w[2]};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int b = 3 * (FLIP ? 3 - k : k) + ch;                  // which of the 12 bytes
+            const uint32_t u = (w3[b >> 2] >> (8 * (b & 3))) & 255u;
+            v[k] = USE_TAB ? tab[ch * 256 + u] : fmaf((float)u, P.scale[ch], P.bias[ch]);
+        }
+        store_plane4<OUT>(o + ch * plane, v, true, 4);
+    }
+}
+
+// pad[ch] = normalised value of a zero byte (RandomCrop padding is applied to the augmented image)
+template <int OUT, bool USE_TAB>
+__device__ __forceinline__ void final_rows_stream(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
+                                                  const TailInfo& t, void* out_img, int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const uint32_t qpr = (uint32_t)P.out_w >> 2;
+    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
+    FastDiv dq; dq.init(qpr, P.rcp_out_qpr);
+    uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
+    const uint32_t dr = dq.div(blockDim.x), dx = blockDim.x - dr * qpr;
+    const uint32_t plane = (uint32_t)P.out_h * (uint32_t)P.out_w;
+    const bool flip = t.flip != 0;
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int ox0 = (int)qx * 4, oy = oy0 + (int)r;
+        const int sx0 = (flip ? (P.out_w - 4 - ox0) : ox0) + t.crop_dx, ay = oy + t.crop_dy;
+        T* o = reinterpret_cast<T*>(out_img) + (uint32_t)(oy * P.out_w + ox0);
+        if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(c.sraw + ((uint32_t)(ay * c.W + sx0) * 3u - c.s_lo));
+            if (flip) stream_quad<OUT, USE_TAB, true>(P, w, tab, o, plane);
+            else stream_quad<OUT, USE_TAB, false>(P, w, tab, o, plane);
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float v[4] = {pad[ch], pad[ch], pad[ch], pad[ch]};
+                store_plane4<OUT>(o + ch * plane, v, true, 4);
+            }
+        }
+        qx += dx; r += dr;
+        if (qx >= qpr) { qx -= qpr; ++r; }
+    }
+}
+
+// PLAIN / LUT final pass: the streaming loop when possible, else the generic aligned loop.
+// `ftab` (768 floats) is only read for LUT programs and must hold normalise(ch, lutc[ch][b]).
+template <int OUT, bool TAB, bool LUT>
+__device__ __forceinline__ void final_rows_plain_lut(const AugParams& P, const float* s_norm, const float* ftab, const Ctx& c,
+                                                     const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1) {
+    if constexpr (OUT != OUT_U8_HWC) {
+        if ((!LUT || ftab != nullptr) && band_fully_staged(c, t, oy0, oy1)) {
+            const float pad[3] = {normalise<TAB>(P, s_norm, 0, 0u), normalise<TAB>(P, s_norm, 1, 0u), normalise<TAB>(P, s_norm, 2, 0u)};
+            if (LUT) final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
+            else final_rows_stream<OUT, TAB>(P, s_norm, pad, c, t, out_img, oy0, oy1);
+            return;
+        }
+    }
+    final_rows<OUT, TAB, LUT ? C_LUT : C_PLAIN>(P, s_norm, c, lutc, t, out_img, oy0, oy1);
+}
+
+// ftab[ch][b] = normalise(ch, lutc[ch][b]) (all threads; ends with a barrier)
+template <bool TAB>
+__device__ __forceinline__ void build_ftab(const AugParams& P, const float* s_norm, const uint8_t* lutc, float* ftab) {
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) ftab[i] = normalise<TAB>(P, s_norm, i >> 8, (uint32_t)lutc[i]);
+    __syncthreads();
+}
+
 template <int OUT, bool TAB>
 __device__ __forceinline__ void final_rows_cls(int cls, const AugParams& P, const float* s_norm, const Ctx& c,
-                                               const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1) {
+                                               const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1,
+                                               const float* ftab = nullptr) {
     switch (cls) {
-    case C_PLAIN: final_rows<OUT, TAB, C_PLAIN>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
-    case C_LUT:   final_rows<OUT, TAB, C_LUT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
+    case C_PLAIN: final_rows_plain_lut<OUT, TAB, false>(P, s_norm, ftab, c, lutc, t, out_img, oy0, oy1); break;
+    case C_LUT:   final_rows_plain_lut<OUT, TAB, true>(P, s_norm, ftab, c, lutc, t, out_img, oy0, oy1); break;
     case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     case C_SHARP: final_rows<OUT, TAB, C_SHARP>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
     case C_GEOM:  final_rows<OUT, TAB, C_GEOM>(P, s_norm, c, lutc, t, out_img, oy0, oy1); break;
@@ -896,8 +997,15 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
             final_rows_cls<OUT, TAB>(C_SG, P, s_norm, cg2, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
         } else {
             any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
-            final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
+            // LUT programs: composed LUT o normalisation table in the (now idle) slot-0 histogram
+            float* ftab = nullptr;
+            if (OUT != OUT_U8_HWC && cls == C_LUT) {
+                ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
+                build_ftab<TAB>(P, s_norm, st[0].lutc, ftab);
+            }
+            final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1, ftab);
         }
+        zero_box_rows<OUT>(P, st[0].prog, out_img, oy0, oy1);
     } else {
         const uint8_t* raw1 = P.in + (size_t)src_idx[1] * img_bytes;
         const Ctx c0 = make_ctx(P, raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], true);
@@ -923,6 +1031,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     __shared__ Prog s_prog;
     __shared__ __align__(16) uint8_t s_lut[2][768];
     __shared__ __align__(16) uint8_t s_lutc[768];
+    __shared__ float s_ftab[OUT == OUT_U8_HWC ? 1 : 768];       // LUT programs: normalise(ch, lutc[ch][b])
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_img;
@@ -956,6 +1065,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
                 if (lut_mask & 1u) v = s_lut[0][base + v];
                 if (lut_mask & 2u) v = s_lut[1][base + v];
                 s_lutc[i] = (uint8_t)v;
+                if constexpr (OUT != OUT_U8_HWC) s_ftab[i] = normalise<TAB>(P, s_norm, i >> 8, v);
             }
             __syncthreads();
         }
@@ -975,11 +1085,12 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
     switch (cls) {
-    case C_PLAIN: final_rows<OUT, TAB, C_PLAIN>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
-    case C_LUT:   final_rows<OUT, TAB, C_LUT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    case C_PLAIN: final_rows_plain_lut<OUT, TAB, false>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
+    case C_LUT:   final_rows_plain_lut<OUT, TAB, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
     case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
     default:      final_rows<OUT, TAB, C_GEOM>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
     }
+    zero_box_rows<OUT>(P, s_prog, out_img, oy0, oy1);
 }
 
 // out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math (aug_mixup.py:13-23)

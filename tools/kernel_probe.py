@@ -18,7 +18,7 @@ H, W, B = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (224, 224, 
 x = [torch.from_numpy(bench.synth_batch(B, H, W, 1 + i)).cuda() for i in range(4)]
 
 
-def timeit(name, policies, tail, n=200):
+def timeit(name, policies, tail, n=int(os.environ.get("PROBE_N", "200"))):
     pol = CompiledPolicy(policies)
     f = FusedAugmenter(pol, tail, H, W, 1)
     outs = [f.empty_out(B) for _ in range(4)]
