@@ -116,11 +116,16 @@ FAA_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 FAA_HD uint32_t blend_u8(uint32_t deg, uint32_t px, float alpha, bool clip) {
     float d = (float)(int)deg;
     float t = f_add(d, f_mul(alpha, (float)((int)px - (int)deg)));
-    if (clip) {
-        if (t <= 0.0f) return 0u;
-        if (t >= 255.0f) return 255u;
-    }
+    // Saturating truncation serves both cases: for alpha in [0,1] (no clip in Pillow) t already lies
+    // between deg and px - the product is no larger than px-deg and both ends are representable.
+    (void)clip;
+#if defined(__CUDA_ARCH__)
+    return min(__float2uint_rz(t), 255u);
+#else
+    if (t <= 0.0f) return 0u;
+    if (t >= 255.0f) return 255u;
     return (uint32_t)(int)t;
+#endif
 }
 
 // Pillow RGB->L (Convert.c rgb2l): ImageEnhance.Color / Contrast degenerate images.

@@ -405,7 +405,8 @@ __device__ __forceinline__ void point4_any(int pv, const Ctx& c, uint32_t q[4], 
 
 // aligned classes: the four source pixels of an output quad are 12 contiguous bytes.
 // `slot` is the op slot a C_SHARP program's Sharpness sits in (0) / its pointwise follower (1).
-template <int CLS>
+// STAGED (C_SHARP): the three source rows of every quad of the band are inside the staged copy
+template <int CLS, bool STAGED = false>
 __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, const TailInfo& t, int out_w, int ox0,
                                          int oy, uint32_t px[4], int pv = 0) {
     const int sx0 = (t.flip ? (out_w - 4 - ox0) : ox0) + t.crop_dx;
@@ -416,13 +417,15 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
         if (CLS == C_SHARP) {
             const uint32_t pitch = (uint32_t)c.W * 3u;
             const bool rowb = ay == 0 || ay == c.H - 1;
-            const uint8_t* r0 = src_ptr(c, off);
-            const uint8_t* rm = rowb ? r0 : src_ptr(c, off - pitch);
-            const uint8_t* rp = rowb ? r0 : src_ptr(c, off + pitch);
+            const uint8_t* r0 = STAGED ? c.sraw + (off - c.s_lo) : src_ptr(c, off);
+            const uint8_t* rm = rowb ? r0 : (STAGED ? r0 - pitch : src_ptr(c, off - pitch));
+            const uint8_t* rp = rowb ? r0 : (STAGED ? r0 + pitch : src_ptr(c, off + pitch));
             sharp_quad(rm, r0, rp, sx0 > 0, sx0 + 4 < c.W, rowb, sx0 == 0, sx0 + 4 == c.W,
                        bits_to_float(c.op[0].a[0]), c.op[0].a[1] != 0, q);
+            if (pv) {                                   // CTA-uniform: a pointwise op follows the Sharpness
 #pragma unroll
-            for (int k = 0; k < 4; ++k) q[k] = apply_pointwise(c, 1, q[k], sx0 + k, ay);
+                for (int k = 0; k < 4; ++k) q[k] = apply_pointwise(c, 1, q[k], sx0 + k, ay);
+            }
         } else {
             load12(c, off, q);
             if (CLS == C_LUT) {
@@ -585,6 +588,14 @@ __device__ __forceinline__ void emit_quad(const AugParams& P, const float* s_nor
     }
 }
 
+// are all source rows of output rows [oy0, oy1) inside the staged copy of the band?
+__device__ __forceinline__ bool band_fully_staged(const Ctx& c, const TailInfo& t, int oy0, int oy1) {
+    const int a0 = max(oy0 + t.crop_dy, 0), a1 = min(oy1 + t.crop_dy, c.H);        // source rows [a0, a1)
+    if (a1 <= a0) return true;
+    const uint32_t pitch = (uint32_t)c.W * 3u, s_len = c.s_len2 ? c.s_len2 + 2u : 0u;
+    return s_len != 0u && (uint32_t)a0 * pitch >= c.s_lo && (uint32_t)a1 * pitch <= c.s_lo + s_len;
+}
+
 // output rows [oy0, oy1) of one image through the class-specialised evaluator
 template <int OUT, bool TAB, int CLS>
 __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_norm, const Ctx& c, const uint8_t* lutc,
@@ -600,6 +611,8 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
     GeomOp go; int gv = 0;
     if (CLS == C_GEOM || CLS == C_SG) gv = geom_setup(c, t, P.H, P.W, P.out_h, P.out_w, go);
     if (CLS == C_POINT) gv = 4 * point_kind(c.op[0].kind) + point_kind(c.op[1].kind);
+    if (CLS == C_SHARP) gv = c.op[1].kind != K_NONE;
+    const bool staged = CLS == C_SHARP && band_fully_staged(c, t, oy0 - 1, oy1 + 1);
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
         const int ox0 = (int)qx * 4;
         const int oy = oy0 + (int)r;
@@ -607,6 +620,7 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
         else if (CLS == C_GEOM) quad_geom_any<false>(gv, c, go, t, P.out_w, ox0, oy, px);
         else if (CLS == C_SG) quad_geom_any<true>(gv, c, go, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_SHARP && staged) quad_vec<CLS, true>(c, lutc, t, P.out_w, ox0, oy, px, gv);
         else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px, gv);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, vec);
         qx += dx; r += dr;
@@ -641,12 +655,6 @@ __device__ __forceinline__ void zero_box_rows(const AugParams& P, const Prog& g,
 // ---- streaming loop of the PLAIN / LUT classes -------------------------------------------------
 // When every source row of the band is staged, the twelve bytes of a quad go straight from the staged
 // words to the three planes: value = tab[ch][byte] (LUT composed with the normalisation) or the fma.
-__device__ __forceinline__ bool band_fully_staged(const Ctx& c, const TailInfo& t, int oy0, int oy1) {
-    const int a0 = max(oy0 + t.crop_dy, 0), a1 = min(oy1 + t.crop_dy, c.H);        // source rows [a0, a1)
-    if (a1 <= a0) return true;
-    const uint32_t pitch = (uint32_t)c.W * 3u, s_len = c.s_len2 ? c.s_len2 + 2u : 0u;
-    return s_len != 0u && (uint32_t)a0 * pitch >= c.s_lo && (uint32_t)a1 * pitch <= c.s_lo + s_len;
-}
 
 template <int OUT, bool USE_TAB, bool FLIP>
 __device__ __forceinline__ void stream_quad(const AugParams& P, const uint32_t* w, const float* tab,
@@ -759,7 +767,7 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
             switch (cls0) {
             case C_LUT:   quad_vec<C_LUT>(c, lut0, id, W, x0, y, p); break;
             case C_POINT: quad_vec<C_POINT>(c, lut0, id, W, x0, y, p, 4 * point_kind(c.op[0].kind) + point_kind(c.op[1].kind)); break;
-            case C_SHARP: quad_vec<C_SHARP>(c, lut0, id, W, x0, y, p); break;
+            case C_SHARP: quad_vec<C_SHARP>(c, lut0, id, W, x0, y, p, c.op[1].kind != K_NONE); break;
             case C_GEOM:  quad_geom_any<false>(gv, c, go, id, W, x0, y, p); break;
             default:
 #pragma unroll
@@ -900,11 +908,11 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
         uint32_t pa[4], pb[4];
         if (cls0 == C_GENERIC || cls0 == C_GEOM || cls0 == C_SG) quad_generic(c0, t0, P.out_w, ox0, oy, pa);
         else if (cls0 == C_LUT) quad_vec<C_LUT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
-        else if (cls0 == C_SHARP) quad_vec<C_SHARP>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa);
+        else if (cls0 == C_SHARP) quad_vec<C_SHARP>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa, c0.op[1].kind != K_NONE);
         else quad_vec<C_POINT>(c0, st[0].lutc, t0, P.out_w, ox0, oy, pa, 4 * point_kind(c0.op[0].kind) + point_kind(c0.op[1].kind));
         if (cls1 == C_GENERIC || cls1 == C_GEOM || cls1 == C_SG) quad_generic(c1, t1, P.out_w, ox0, oy, pb);
         else if (cls1 == C_LUT) quad_vec<C_LUT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
-        else if (cls1 == C_SHARP) quad_vec<C_SHARP>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb);
+        else if (cls1 == C_SHARP) quad_vec<C_SHARP>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb, c1.op[1].kind != K_NONE);
         else quad_vec<C_POINT>(c1, st[1].lutc, t1, P.out_w, ox0, oy, pb, 4 * point_kind(c1.op[0].kind) + point_kind(c1.op[1].kind));
         const uint32_t za = zero_mask(t0, ox0, oy), zb = zero_mask(t1, ox0, oy);
         const int nvalid = min(4, P.out_w - ox0);
