@@ -217,6 +217,24 @@ __device__ void accumulate_stats(const Ctx& c, bool want_hist, bool want_mean, i
         for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
             uint32_t q[4];
             load12(c, base + 12u * i, q);
+            if (want_hist) {
+                // flat regions (worst case: a constant image) would serialise every shared-memory atomic
+                // 32 ways: when the warp's 128 pixels are one colour, one lane adds the whole count
+                const uint32_t act = __activemask();
+                const int lead = __ffs(act) - 1;
+                const bool flat = (q[0] == q[1]) & (q[1] == q[2]) & (q[2] == q[3]) &
+                                  (__shfl_sync(act, q[0], lead) == q[0]);
+                if (__all_sync(act, flat)) {
+                    if (want_mean) local += 4u * luma_of(q[0]);
+                    if ((int)(threadIdx.x & 31) == lead) {
+                        const uint32_t n = 4u * (uint32_t)__popc(act);
+                        atomicAdd(&hist[q[0] & 255u], n);
+                        atomicAdd(&hist[256u + ((q[0] >> 8) & 255u)], n);
+                        atomicAdd(&hist[512u + (q[0] >> 16)], n);
+                    }
+                    continue;
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (want_mean) local += luma_of(q[k]);
@@ -442,21 +460,30 @@ __device__ __forceinline__ void quad_vec(const Ctx& c, const uint8_t* lutc, cons
 
 // C_GEOM: exactly one geometric op (slot g) and otherwise pointwise ops: the fixed-point source
 // coordinate is stepped along the quad instead of being re-derived per pixel
-__device__ __forceinline__ uint32_t load_raw_cg(const Ctx& c, int x, int y) {     // scratch written by this kernel
-    const uint8_t* p = c.raw + (uint32_t)(y * c.W + x) * 3u;
-    // plain weak loads: the cluster barrier that precedes them invalidates L1 (fence scope >= cluster),
-    // so they are coherent with the peers' stores and still L1-cached for the gather's locality
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-}
 // The geometric op of a C_GEOM / C_SG program as plain registers (no indexed access to the op array).
 struct GeomOp {
     int a0, a1, a2, a3, a4, a5;   // K_AFFINE: 16.16 coefficients; K_SHIFT: a0=dx a1=dy a2=bx a3=by
     int pk;                       // kind of the pointwise op in the other slot (K_NONE: nothing)
 };
 
+// Branch-free fetch of source pixel (x, y) when `ok` (else 0): the staged copy or global memory through ONE
+// generic pointer, so the twelve byte loads of a quad issue back to back - one exposed load latency per
+// quad instead of one per pixel (a warp issues in order and would stall at each pixel's first use).
+__device__ __forceinline__ uint32_t load_raw_sel(const Ctx& c, int x, int y, bool ok) {
+    const uint32_t off = ok ? (uint32_t)(y * c.W + x) * 3u : 0u;
+    const uint32_t rel = off - c.s_lo;
+    const uint8_t* p = (rel < c.s_len2) ? c.sraw + rel : c.raw + off;
+    const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    return ok ? v : 0u;
+}
+
 // G = slot of the geometric op, AFF = it is a K_AFFINE (else K_SHIFT), SIMPLE = the tail is the identity
-// apart from the flip (no crop, out size == image size, out_w % 4 == 0): every pixel of the quad exists
-template <int G, bool AFF, bool SIMPLE, bool COH>
+// apart from the flip (no crop, out size == image size, out_w % 4 == 0): every pixel of the quad exists.
+// COH: the source is the scratch image written by this kernel (plain loads behind the cluster barrier:
+// the barrier's fence invalidates L1, so they are coherent with the peers' stores and still L1-cached).
+// NB: the branch-free fetch (latency-bound cluster kernel); the streaming kernel has enough warps in flight
+// and is issue-bound, there the branchy per-pixel fetch (fewer instructions) is faster.
+template <int G, bool AFF, bool SIMPLE, bool COH, bool NB>
 __device__ __forceinline__ void quad_geom(const Ctx& c, const GeomOp& o, const TailInfo& t, int out_w, int ox0, int oy,
                                           uint32_t px[4]) {
     const int ay = SIMPLE ? oy : oy + t.crop_dy;
@@ -469,38 +496,67 @@ __device__ __forceinline__ void quad_geom(const Ctx& c, const GeomOp& o, const T
         dfx = sx * o.a0; dfy = sx * o.a3;
     }
     const int ysh = AFF ? 0 : ay + o.a1 + (ay >= o.a3);
+    if (!NB) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int ax = ax0 + sx * k;
-        uint32_t p = 0u;
-        const bool have = SIMPLE || (row_ok && (unsigned)ax < (unsigned)c.W && ox0 + k < out_w);
-        if (have) {                                      // (ax, ay) is a pixel of the augmented image
-            int xs, ys;
-            if (AFF) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
-            else { xs = ax + o.a0 + (ax >= o.a2); ys = ysh; }
-            if ((unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H) {
-                p = COH ? load_raw_cg(c, xs, ys) : load_raw(c, xs, ys);
-                if (G == 1 && o.pk != K_NONE) p = apply_pointwise(c, 0, p, xs, ys);     // op0 ran before the gather
+        for (int k = 0; k < 4; ++k) {
+            const int ax = ax0 + sx * k;
+            uint32_t p = 0u;
+            const bool have = SIMPLE || (row_ok && (unsigned)ax < (unsigned)c.W && ox0 + k < out_w);
+            if (have) {                                      // (ax, ay) is a pixel of the augmented image
+                int xs, ys;
+                if (AFF) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
+                else { xs = ax + o.a0 + (ax >= o.a2); ys = ysh; }
+                if ((unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H) {
+                    p = load_raw(c, xs, ys);
+                    if (G == 1 && o.pk != K_NONE) p = apply_pointwise(c, 0, p, xs, ys);     // op0 ran before the gather
+                }
+                if (G == 0 && o.pk != K_NONE) p = apply_pointwise(c, 1, p, ax, ay);         // op1 runs after it (fill included)
             }
-            if (G == 0 && o.pk != K_NONE) p = apply_pointwise(c, 1, p, ax, ay);         // op1 runs after it (fill included)
+            px[k] = p;
         }
-        px[k] = p;
+        return;
+    }
+    uint32_t have_m = 0, ins_m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                        // 1. the four fetches, no branches in between
+        const int ax = ax0 + sx * k;
+        const bool have = SIMPLE || (row_ok && (unsigned)ax < (unsigned)c.W && ox0 + k < out_w);   // a pixel of the augmented image
+        int xs, ys;
+        if (AFF) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
+        else { xs = ax + o.a0 + (ax >= o.a2); ys = ysh; }
+        const bool ins = have && (unsigned)xs < (unsigned)c.W && (unsigned)ys < (unsigned)c.H;
+        px[k] = load_raw_sel(c, xs, ys, ins);
+        have_m |= (uint32_t)have << k; ins_m |= (uint32_t)ins << k;
+    }
+    if (o.pk != K_NONE) {                                // 2. the pointwise op of the other slot (CTA-uniform)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ax = ax0 + sx * k;
+            if (G == 1) {                                // op0 ran before the gather: at the source position
+                int xs, ys;
+                if (AFF) { xs = (fx + k * dfx) >> 16; ys = (fy + k * dfy) >> 16; }
+                else { xs = ax + o.a0 + (ax >= o.a2); ys = ysh; }
+                if ((ins_m >> k) & 1u) px[k] = apply_pointwise(c, 0, px[k], xs, ys);
+            } else {                                     // op1 runs after it (fill included)
+                if ((have_m >> k) & 1u) px[k] = apply_pointwise(c, 1, px[k], ax, ay);
+            }
+        }
     }
 }
 
 // runtime -> compile-time dispatch of the variants (CTA-uniform), one call per quad
-template <bool COH>
+template <bool COH, bool NB>
 __device__ __forceinline__ void quad_geom_any(int variant, const Ctx& c, const GeomOp& o, const TailInfo& t, int out_w,
                                               int ox0, int oy, uint32_t px[4]) {
     switch (variant) {
-    case 0: quad_geom<0, false, false, COH>(c, o, t, out_w, ox0, oy, px); break;
-    case 1: quad_geom<0, false, true, COH>(c, o, t, out_w, ox0, oy, px); break;
-    case 2: quad_geom<0, true, false, COH>(c, o, t, out_w, ox0, oy, px); break;
-    case 3: quad_geom<0, true, true, COH>(c, o, t, out_w, ox0, oy, px); break;
-    case 4: quad_geom<1, false, false, COH>(c, o, t, out_w, ox0, oy, px); break;
-    case 5: quad_geom<1, false, true, COH>(c, o, t, out_w, ox0, oy, px); break;
-    case 6: quad_geom<1, true, false, COH>(c, o, t, out_w, ox0, oy, px); break;
-    default: quad_geom<1, true, true, COH>(c, o, t, out_w, ox0, oy, px); break;
+    case 0: quad_geom<0, false, false, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    case 1: quad_geom<0, false, true, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    case 2: quad_geom<0, true, false, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    case 3: quad_geom<0, true, true, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    case 4: quad_geom<1, false, false, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    case 5: quad_geom<1, false, true, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    case 6: quad_geom<1, true, false, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
+    default: quad_geom<1, true, true, COH, NB>(c, o, t, out_w, ox0, oy, px); break;
     }
 }
 
@@ -597,7 +653,7 @@ __device__ __forceinline__ bool band_fully_staged(const Ctx& c, const TailInfo& 
 }
 
 // output rows [oy0, oy1) of one image through the class-specialised evaluator
-template <int OUT, bool TAB, int CLS>
+template <int OUT, bool TAB, int CLS, bool NB = true>
 __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_norm, const Ctx& c, const uint8_t* lutc,
                                            const TailInfo& t, void* out_img, int oy0, int oy1) {
     const uint32_t qpr = (uint32_t)(P.out_w + 3) >> 2;
@@ -618,8 +674,8 @@ __device__ __forceinline__ void final_rows(const AugParams& P, const float* s_no
         const int oy = oy0 + (int)r;
         uint32_t px[4];
         if (CLS == C_GENERIC) quad_generic(c, t, P.out_w, ox0, oy, px);
-        else if (CLS == C_GEOM) quad_geom_any<false>(gv, c, go, t, P.out_w, ox0, oy, px);
-        else if (CLS == C_SG) quad_geom_any<true>(gv, c, go, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_GEOM) quad_geom_any<false, NB>(gv, c, go, t, P.out_w, ox0, oy, px);
+        else if (CLS == C_SG) quad_geom_any<true, true>(gv, c, go, t, P.out_w, ox0, oy, px);
         else if (CLS == C_SHARP && staged) quad_vec<CLS, true>(c, lutc, t, P.out_w, ox0, oy, px, gv);
         else quad_vec<CLS>(c, lutc, t, P.out_w, ox0, oy, px, gv);
         emit_quad<OUT, TAB>(P, s_norm, out_img, ox0, oy, px, vec);
@@ -768,7 +824,7 @@ __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* 
             case C_LUT:   quad_vec<C_LUT>(c, lut0, id, W, x0, y, p); break;
             case C_POINT: quad_vec<C_POINT>(c, lut0, id, W, x0, y, p, 4 * point_kind(c.op[0].kind) + point_kind(c.op[1].kind)); break;
             case C_SHARP: quad_vec<C_SHARP>(c, lut0, id, W, x0, y, p, c.op[1].kind != K_NONE); break;
-            case C_GEOM:  quad_geom_any<false>(gv, c, go, id, W, x0, y, p); break;
+            case C_GEOM:  quad_geom_any<false, true>(gv, c, go, id, W, x0, y, p); break;
             default:
 #pragma unroll
                 for (int k = 0; k < 4; ++k) p[k] = Level<1>::at(c, x0 + k, y);
@@ -1096,7 +1152,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     case C_PLAIN: final_rows_plain_lut<OUT, TAB, false>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
     case C_LUT:   final_rows_plain_lut<OUT, TAB, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
     case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
-    default:      final_rows<OUT, TAB, C_GEOM>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    default:      final_rows<OUT, TAB, C_GEOM, false>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
     }
     zero_box_rows<OUT>(P, s_prog, out_img, oy0, oy1);
 }
