@@ -287,9 +287,13 @@ __device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool want_hist,
     }
     if (want_mean) {
         unsigned long long t = 0;
-        for (int r = 0; r < bands; ++r) {
-            const unsigned long long* rem = (bands > 1) ? cluster.map_shared_rank(&st.suml[j], r) : &st.suml[j];
-            t += *rem;
+        if (bands > 1) {
+            unsigned long long v[8];                                // all remote loads in flight together
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = r < bands ? *cluster.map_shared_rank(&st.suml[j], r) : 0ull;
+            t = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        } else {
+            t = st.suml[j];
         }
         mean = contrast_mean(t, n_pixels);
     }
