@@ -217,24 +217,6 @@ __device__ void accumulate_stats(const Ctx& c, bool want_hist, bool want_mean, i
         for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
             uint32_t q[4];
             load12(c, base + 12u * i, q);
-            if (want_hist) {
-                // flat regions (worst case: a constant image) would serialise every shared-memory atomic
-                // 32 ways: when the warp's 128 pixels are one colour, one lane adds the whole count
-                const uint32_t act = __activemask();
-                const int lead = __ffs(act) - 1;
-                const bool flat = (q[0] == q[1]) & (q[1] == q[2]) & (q[2] == q[3]) &
-                                  (__shfl_sync(act, q[0], lead) == q[0]);
-                if (__all_sync(act, flat)) {
-                    if (want_mean) local += 4u * luma_of(q[0]);
-                    if ((int)(threadIdx.x & 31) == lead) {
-                        const uint32_t n = 4u * (uint32_t)__popc(act);
-                        atomicAdd(&hist[q[0] & 255u], n);
-                        atomicAdd(&hist[256u + ((q[0] >> 8) & 255u)], n);
-                        atomicAdd(&hist[512u + (q[0] >> 16)], n);
-                    }
-                    continue;
-                }
-            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (want_mean) local += luma_of(q[k]);
