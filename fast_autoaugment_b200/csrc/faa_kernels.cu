@@ -63,7 +63,9 @@ struct FastDiv {
 };
 
 // ---------------------------------------------------------------------------------------
-// launch 1
+// launch 1 (main translation unit only; the pixel kernels are compiled once per output type, in parallel:
+// -DFAA_TU_OUT=<OutType> builds just launch_out<that type>, see __graft_entry__.build)
+#ifndef FAA_TU_OUT
 __device__ __forceinline__ int cost_bucket(uint32_t cost) {     // 0 = most expensive
     int b = kCostBuckets - 1;
     uint32_t th = 4u;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
         P.order[P.first + s_base[b] + atomicAdd(&s_count[b], 1)] = t;
     }
 }
+
+#endif  // !FAA_TU_OUT
 
 // ---------------------------------------------------------------------------------------
 // TMA 1-D bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
@@ -240,7 +244,7 @@ __device__ void accumulate_stats(const Ctx& c, bool want_hist, bool want_mean, i
 }
 
 // cluster-wide totals of slot j's partial statistics: histogram -> st.tot (every CTA), luma -> mean
-__device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool want_hist, bool want_mean, ImgState& st, int j,
+static __device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool want_hist, bool want_mean, ImgState& st, int j,
                                    cg::cluster_group& cluster) {
     uint32_t mean = 0;
     if (bands > 1) cluster.sync(); else __syncthreads();         // partials complete everywhere
@@ -285,7 +289,7 @@ __device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool want_hist,
 }
 
 // slot j's 3x256 LUT from st.tot (histogram ops) or from the op's parameters (+ mean)
-__device__ void make_lut(uint32_t n_pixels, ImgState& st, int j, uint32_t mean) {
+static __device__ void make_lut(uint32_t n_pixels, ImgState& st, int j, uint32_t mean) {
     const OpRec o = st.prog.op[j];
     const int kind = o.kind;
     if (kind_needs_hist(kind)) {
@@ -318,7 +322,7 @@ __device__ __forceinline__ void compose_lut(ImgState& st, uint32_t lut_mask) {
 }
 
 // everything before the final pass for one (non-MAT) source image
-__device__ bool prepare_image(const AugParams& P, const Ctx& c, int y0, int y1, ImgState& st, cg::cluster_group& cluster) {
+static __device__ bool prepare_image(const AugParams& P, const Ctx& c, int y0, int y1, ImgState& st, cg::cluster_group& cluster) {
     const uint32_t stat_mask = st.prog.stat_mask, lut_mask = st.prog.lut_mask;
     if (lut_mask == 0) return false;
     const uint32_t n_pixels = (uint32_t)P.H * (uint32_t)P.W;
@@ -794,7 +798,7 @@ constexpr uint32_t kMatGuard = 16;
 // op0 nine times (lazy Sharpness) and keeps shared memory bounded for any image size.
 // rows [r0, r1) of op0's output (op1 disabled in `c`) -> dst (+ row pitch), through the
 // class-specialised single-op evaluators (cls0) when the width allows 4-pixel quads
-__device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* dst, int r0, int r1) {
+static __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* dst, int r0, int r1) {
     const int W = c.W;
     if ((W & 3) == 0) {
         const uint32_t qpr = (uint32_t)W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
@@ -1143,6 +1147,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     zero_box_rows<OUT>(P, s_prog, out_img, oy0, oy1);
 }
 
+#ifndef FAA_TU_OUT
 // out[i] = data[i]*lam + data[perm[i]]*(1-lam), fp32 math (aug_mixup.py:13-23)
 template <typename T>
 __global__ void faa_mixup_kernel(const T* __restrict__ data, T* __restrict__ out, const int64_t* __restrict__ perm,
@@ -1193,6 +1198,8 @@ uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
     return (cap + 127u) & ~127u;
 }
 
+#endif  // !FAA_TU_OUT
+
 template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     const size_t dyn = (size_t)p.geo[0].band_cap * NSRC + (size_t)p.mat_cap;
@@ -1235,11 +1242,21 @@ static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
 }
 
 template <int OUT>
-static cudaError_t launch_out(const AugParams& p, bool mix, bool tab, bool light, cudaStream_t stream) {
+cudaError_t launch_out(const AugParams& p, bool mix, bool tab, bool light, cudaStream_t stream) {
     if (light) return tab ? launch_light<OUT, true>(p, stream) : launch_light<OUT, false>(p, stream);
-    if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
+    if constexpr (OUT != OUT_U8_HWC) {                   // fused Mixup needs a float output
+        if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
+    }
     return tab ? launch_one<OUT, 1, true>(p, stream) : launch_one<OUT, 1, false>(p, stream);
 }
+
+#ifdef FAA_TU_OUT
+template cudaError_t launch_out<FAA_TU_OUT>(const AugParams&, bool, bool, bool, cudaStream_t);
+#else
+extern template cudaError_t launch_out<OUT_F16>(const AugParams&, bool, bool, bool, cudaStream_t);
+extern template cudaError_t launch_out<OUT_BF16>(const AugParams&, bool, bool, bool, cudaStream_t);
+extern template cudaError_t launch_out<OUT_F32>(const AugParams&, bool, bool, bool, cudaStream_t);
+extern template cudaError_t launch_out<OUT_U8_HWC>(const AugParams&, bool, bool, bool, cudaStream_t);
 
 // light == false: the cluster kernel (all images, or the heavy part of a split launch);
 // light == true : the streaming kernel for the light part of a split launch (p.n_heavy != nullptr)
@@ -1276,5 +1293,7 @@ cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int b
     }
     return cudaGetLastError();
 }
+
+#endif  // FAA_TU_OUT
 
 }  // namespace faa
