@@ -329,15 +329,16 @@ def test_translate_accumulator_break():
     assert np.array_equal(got, want)
 
 
-def test_resolve_ahead_and_split_paths_are_invisible():
+@pytest.mark.parametrize("B,H,W,cutout,dtype", [(96, 224, 224, 0, torch.float16), (32, 380, 380, 16, torch.bfloat16)])
+def test_resolve_ahead_and_split_paths_are_invisible(B, H, W, cutout, dtype):
     """fused Philox launches at a size that takes the split (light + cluster kernel) path, called
     back to back so that the resolve-ahead speculation hits, with a stride change and a seed change
-    in the sequence: every result must equal the one computed from the device sampler's records"""
+    in the sequence: every result must equal the one computed from the device sampler's records
+    (second case: CutoutDefault boxes - the post-pass of both pixel kernels - and bf16 output)"""
     import ctypes as C
     from fast_autoaugment_b200.engine import FusedAugmenter
     policies = archive.fa_resnet50_rimagenet()
-    tail = TailSpec.imagenet(0, torch.float16)
-    B, H, W = 96, 224, 224
+    tail = TailSpec.imagenet(cutout, dtype)
     x = dev(synth_batch(B, (H, W), seed=21))
     pol = CompiledPolicy(policies)
     f = FusedAugmenter(pol, tail, H, W, seed=5)
