@@ -986,7 +986,6 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     __shared__ ImgState st[NSRC];
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar[NSRC];
-    __shared__ int s_img;
 
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
@@ -1000,9 +999,8 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
 
     // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule
     if (P.n_heavy != nullptr && (int)blockIdx.y >= *P.n_heavy) return;      // cluster-uniform
-    if (threadIdx.x == 0) s_img = P.order ? P.order[P.first + blockIdx.y] : (int)blockIdx.y;     // LPT schedule
-    __syncthreads();
-    const int img = s_img;
+    // LPT schedule entry: a uniform load per warp (no shared-memory hand-off, no barrier)
+    const int img = P.order ? __ldg(P.order + P.first + blockIdx.y) : (int)blockIdx.y;
     int src_idx[NSRC];
     src_idx[0] = P.first + img;
     if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
@@ -1088,7 +1086,6 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     __shared__ float s_ftab[OUT == OUT_U8_HWC ? 1 : 768];       // LUT programs: normalise(ch, lutc[ch][b])
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_img;
 
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
@@ -1097,9 +1094,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     const int n_heavy = *P.n_heavy;
     if ((int)blockIdx.y >= P.B - n_heavy) return;
-    if (threadIdx.x == 0) s_img = P.order[P.first + n_heavy + blockIdx.y];
-    __syncthreads();
-    const int img = s_img;
+    const int img = __ldg(P.order + P.first + n_heavy + blockIdx.y);     // uniform load per warp
     const int idx = P.first + img;
     if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)idx * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
