@@ -211,8 +211,9 @@ __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t p) {
 // statistics of the image in front of slot L (0 or 1) over rows [y0, y1):
 // per-channel histogram and / or the luma sum
 template <int L>
-__device__ void accumulate_stats(const Ctx& c, bool want_hist, bool want_mean, int y0, int y1, uint32_t* hist,
+__device__ void accumulate_stats(const Ctx& c_in, bool want_hist, bool want_mean, int y0, int y1, uint32_t* hist,
                                  unsigned long long* suml) {
+    const Ctx c = c_in;                 // private copy: no local-memory loads through the reference in the loop
     uint32_t local = 0;
     if (L == 0 && (c.W & 3) == 0) {
         // raw image: 4 pixels per thread from 12 aligned bytes
@@ -798,7 +799,10 @@ constexpr uint32_t kMatGuard = 16;
 // op0 nine times (lazy Sharpness) and keeps shared memory bounded for any image size.
 // rows [r0, r1) of op0's output (op1 disabled in `c`) -> dst (+ row pitch), through the
 // class-specialised single-op evaluators (cls0) when the width allows 4-pixel quads
-static __device__ void fill_rows(const Ctx& c, int cls0, const uint8_t* lut0, uint8_t* dst, int r0, int r1) {
+static __device__ void fill_rows(const Ctx& c_in, int cls0, const uint8_t* lut0, uint8_t* dst, int r0, int r1) {
+    // a private copy: through the reference every field read in the loop is a local-memory load (the caller's
+    // stack frame), and with most of the SM's L1 carved out as shared memory those go to L2
+    const Ctx c = c_in;
     const int W = c.W;
     if ((W & 3) == 0) {
         const uint32_t qpr = (uint32_t)W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
