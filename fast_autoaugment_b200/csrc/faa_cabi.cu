@@ -219,7 +219,24 @@ struct faa_policy {
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaStream_t light_stream = nullptr; cudaEvent_t ev_res = nullptr, ev_light = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int device = -1;                     // the device that owns every buffer / stream / event above (-1: none yet)
+    int32_t ticket = 0;                  // chained steps: id of the last resolve launch
+    int32_t ahead_ticket = 0;
+    cudaStream_t chain_stream = nullptr; bool chain_live = false;   // the previous call was a chained step on this stream
+    uintptr_t prev_out[2] = {0, 0}, prev_in[2] = {0, 0};            // byte ranges the previous chained step wrote / read
 };
+
+// All device state of a policy handle lives on ONE device: the one current at its first device call.
+static int bind_device(faa_policy* p) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(FAA_ERR_NO_DEVICE, "no current CUDA device"); }
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->device < 0) p->device = dev;
+    if (p->device != dev)
+        return fail(FAA_ERR_VALUE, "policy handle is bound to device " + std::to_string(p->device) + " but the current device is " +
+                    std::to_string(dev) + ": create one policy handle per device");
+    return FAA_OK;
+}
 
 static const std::vector<Compiled>& host_table(faa_policy* p, int H, int W) {
     std::lock_guard<std::mutex> lk(p->mu);
@@ -523,6 +540,7 @@ int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t
     if (int e = check_shape(h, w)) return e;
     if (int e = check_tail(tail)) return e;
     if (int e = ensure_device()) return e;
+    if (int e = bind_device(p)) return e;
     const OpRec* d_ops = nullptr;
     if (int e = device_table(p, h, w, true, &d_ops)) return e;
     ResolveParams R; memset(&R, 0, sizeof R);
@@ -549,6 +567,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (tail->out_dtype == FAA_U8_HWC && d_partner) return fail(FAA_ERR_UNSUPPORTED, "mixup needs a float output");
     if (int e = ensure_device()) return e;
     if (batch == 0) return FAA_OK;
+    if (int e = bind_device(p)) return e;
     cudaStream_t stream = (cudaStream_t)stream_v;
     const OpRec* d_ops = nullptr;
     // resolved samples can only reference ops the host sampler validated; Philox can pick anything
@@ -565,7 +584,8 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             }
             need = need < 65536 ? 65536 : need * 2;
             CK(cudaMalloc(&p->d_progs, 2 * need));                                                // two slots (resolve-ahead)
-            CK(cudaMalloc(&p->d_order, 2 * (2 * (need / sizeof(Prog)) * sizeof(int32_t) + 16)));  // order + per-launch counters, x2
+            CK(cudaMalloc(&p->d_order, 2 * (3 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));  // order + per-launch counters + ready words, x2
+            CK(cudaMemset(p->d_order, 0, 2 * (3 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));
             p->d_progs_bytes = need;
             p->ahead_valid = false;
         }
@@ -613,6 +633,10 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         fill_geom(P.geo[1], lb, h, w, tail->out_h, P.crop_pad, P.stage != 0 && (size_t)band_capacity(lb, h, w, tail->out_h, P.crop_pad) <= 100 * 1024);
         auto rcp = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); };
         P.rcp_out_qpr = rcp((uint32_t)(tail->out_w + 3) / 4); P.rcp_w = rcp((uint32_t)w); P.rcp_wq = rcp((uint32_t)w / 4);
+        P.rcp_opr = (w & 7) ? 0u : rcp((uint32_t)w / 8);
+        static const bool oct_off = [] { const char* e = getenv("FAA_OCTETS"); return e && e[0] == '0'; }();
+        P.octets = (!oct_off && (w & 7) == 0 && tail->out_w == w && tail->out_h == h && tail->out_dtype != FAA_U8_HWC &&
+                    ((uintptr_t)d_out % 16) == 0 && P.stage) ? 1 : 0;
     }
     // materialisation chunk: as many rows as fit ~16 KB, at least 3 (single-source launches only)
     {
@@ -637,19 +661,35 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     static const bool ahead_off = [] { const char* e = getenv("FAA_AHEAD"); return e && e[0] == '0'; }();
     const bool use_order = !(d_partner || lpt_off);
     // (small launches are launch-latency bound: one pixel kernel is faster there)
+    size_t split_min = (size_t)4 << 20;                   // pixels per launch from which two pixel kernels pay off
+    if (const char* e = getenv("FAA_SPLIT_MIN")) split_min = (size_t)strtoull(e, nullptr, 10);   // tests: force either path
     const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC &&
-                           (size_t)batch * h * w >= ((size_t)4 << 20);
+                           (size_t)batch * h * w >= split_min;
     R.split = use_split ? 1 : 0;
-    // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[cap]
+    // Chained steps (default for the fused-Philox production path): resolve(N+1), cluster(N), light(N) all on the
+    // caller's stream with programmatic dependent launches, no events and no side streams.  Consecutive steps
+    // overlap (the next step's CTAs fill the slots the previous step's tail frees); the only true dependency -
+    // programs written by the resolve kernel - is a ticket word the pixel kernels poll.  FAA_CHAIN=0: the
+    // two-stream schedule with events (light kernel on the caller's stream, cluster kernel on a priority stream).
+    int chain_mode = 1;
+    if (const char* e = getenv("FAA_CHAIN")) chain_mode = atoi(e);
+    const bool use_chain = chain_mode != 0 && use_split && allow_ahead && rng && !d_samples && !d_partner &&
+                           !(getenv("FAA_AHEAD") && getenv("FAA_AHEAD")[0] == '0');
+    // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[cap] + ready[cap]
     const size_t cap_imgs = p->d_progs_bytes / sizeof(Prog);
     auto bind_slot = [&](int slot, ResolveParams& r, AugParams* a) {
         Prog* progs = reinterpret_cast<Prog*>((uint8_t*)p->d_progs + (size_t)slot * p->d_progs_bytes);
-        int32_t* order = reinterpret_cast<int32_t*>(p->d_order) + (size_t)slot * (2 * cap_imgs + 4);
+        int32_t* order = reinterpret_cast<int32_t*>(p->d_order) + (size_t)slot * (3 * cap_imgs + 8);
         // light programs run in their own streaming kernel; its counter lives behind the order array,
-        // indexed by `first` so that concurrent chunk launches do not share it
+        // indexed by `first` so that concurrent chunk launches do not share it (same for the ready word)
         int32_t* counter = order + cap_imgs + first;
+        int32_t* ready = order + 2 * cap_imgs + first;
         r.progs = progs; r.order = use_order ? order : nullptr; r.n_heavy = use_split ? counter : nullptr;
-        if (a) { a->progs = progs; a->order = use_order ? order : nullptr; a->n_heavy = use_split ? counter : nullptr; }
+        r.ready = use_chain ? ready : nullptr;
+        if (a) {
+            a->progs = progs; a->order = use_order ? order : nullptr; a->n_heavy = use_split ? counter : nullptr;
+            a->ready = use_chain ? ready : nullptr;
+        }
     };
     if (p->has_sg && !d_partner && (w & 3) == 0) {       // scratch images for Sharpness->gather programs
         const size_t need = (size_t)n_all * img_bytes;
@@ -669,11 +709,67 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (spec_ok) {
         key.seed = rng->seed; key.first_index = rng->first_index;
         const int32_t v[16] = {batch, n_all, first, h, w, tail->out_h, tail->out_w, op_base, apply_tail, R.allow, R.split,
-                               rng->crop_pad, rng->hflip, rng->zero_box_len, use_order ? 1 : 0, 0};
+                               rng->crop_pad, rng->hflip, rng->zero_box_len, use_order ? 1 : 0, use_chain ? 1 : 0};
         memcpy(key.v, v, sizeof v);
     }
     const bool hit = spec_ok && p->ahead_valid && memcmp(&key, &p->ahead_key, sizeof key) == 0;
     int slot = p->cur_slot;
+    if (use_chain) {
+        // ---- chained schedule -------------------------------------------------------------------------
+        // A step may only overlap the previous one if it neither reads what that step wrote nor writes what it
+        // read or wrote (and follows it on the same stream); otherwise its first kernel is a plain dependent launch.
+        const uintptr_t in0 = (uintptr_t)d_in_all + (size_t)first * img_bytes, in1 = in0 + (size_t)batch * img_bytes;
+        const uintptr_t out0 = (uintptr_t)d_out, out1 = out0 + (size_t)batch * tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
+        auto overlap = [](uintptr_t a0, uintptr_t a1, const uintptr_t b[2]) { return a0 < b[1] && b[0] < a1; };
+        bool overlap_ok = p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
+                          !overlap(out0, out1, p->prev_out) && !overlap(out0, out1, p->prev_in);
+        AugParams Pc = P;
+        Pc.chain = 1; Pc.pdl = 0;
+        if (hit) {
+            slot = p->ahead_slot;
+            Pc.ticket = p->ahead_ticket;
+            bind_slot(slot, R, &Pc);
+        } else {
+            bind_slot(slot, R, &Pc);
+            R.ticket = ++p->ticket; R.pdl = overlap_ok ? 1 : 0;
+            Pc.ticket = R.ticket;
+            CK(launch_resolve(R, stream));
+            g_launches++;
+            overlap_ok = true;                              // the kernels behind it may overlap IT
+        }
+        p->cur_slot = slot;
+        p->ahead_valid = false;
+        {   // speculate on the next call: same everything, first_index advanced by the stride seen so far
+            uint64_t stride = (uint64_t)batch;
+            faa_policy::AheadKey base = key; base.first_index = 0;
+            faa_policy::AheadKey lastb = p->last_key; lastb.first_index = 0;
+            if (p->have_last && memcmp(&base, &lastb, sizeof base) == 0 && rng->first_index > p->last_key.first_index)
+                stride = rng->first_index - p->last_key.first_index;
+            p->last_key = key; p->have_last = true;
+            ResolveParams R2 = R;
+            R2.rng.first_index = rng->first_index + stride;
+            bind_slot(slot ^ 1, R2, nullptr);
+            R2.ticket = ++p->ticket; R2.pdl = overlap_ok ? 1 : 0;
+            // (its slot's last readers - the step before this one - copied their programs before they let any
+            //  later kernel of the stream start, so the resolve kernel may overwrite the slot as soon as it runs)
+            CK(launch_resolve(R2, stream));
+            g_launches++;
+            p->ahead_key = key; p->ahead_key.first_index = rng->first_index + stride;
+            p->ahead_slot = slot ^ 1; p->ahead_valid = true; p->ahead_ticket = R2.ticket;
+        }
+        if (chain_mode == 2) {
+            CK(launch_augment(Pc, tail->out_dtype, use_tab, true, stream));
+            CK(launch_augment(Pc, tail->out_dtype, use_tab, false, stream));
+        } else {
+            CK(launch_augment(Pc, tail->out_dtype, use_tab, false, stream));
+            CK(launch_augment(Pc, tail->out_dtype, use_tab, true, stream));
+        }
+        g_launches += 2;
+        p->chain_live = true; p->chain_stream = stream;
+        p->prev_in[0] = in0; p->prev_in[1] = in1; p->prev_out[0] = out0; p->prev_out[1] = out1;
+        return FAA_OK;
+    }
+    p->chain_live = false;
     if (hit) {
         slot = p->ahead_slot;
         CK(cudaStreamWaitEvent(stream, p->ev_ahead, 0));
@@ -811,6 +907,7 @@ int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_
     if (int e = check_tail(tail)) return e;
     if (int e = ensure_device()) return e;
     if (batch <= 0) return FAA_OK;
+    if (int e = bind_device(p)) return e;
     cudaStream_t stream = (cudaStream_t)stream_v;
     const size_t in_img = (size_t)h * w * 3;
     const size_t out_img = (size_t)tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);

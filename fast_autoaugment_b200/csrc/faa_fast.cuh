@@ -1,0 +1,412 @@
+// faa_fast.cuh - lean final passes of the light (streaming) kernel for the common launch geometry:
+// W % 8 == 0, output size == image size, no crop (P.octets, TailInfo without crop).  Included by
+// faa_kernels.cu behind the generic evaluators; every routine here has a generic counterpart there that
+// is used whenever its preconditions do not hold, and the GPU parity tests run both.
+//
+//   row-shift gathers   TranslateX/Y(+Abs) and ShearX move whole rows: an output octet (8 pixels) is 24
+//                       contiguous source bytes at an arbitrary byte offset -> seven aligned words and six
+//                       funnel shifts, then the same 16-byte plane stores as the streaming loop
+//                       (augmentations.py:13-17,27-54 through Pillow's affine_fixed / ImagingScaleAffine)
+//   lean affine gather  ShearY / Rotate (augmentations.py:20-24,57-61): four source pixels per thread from
+//                       global memory (L1), no staged-copy test, no branches between the loads
+//   Color               ImageEnhance.Color (augmentations.py:102-104) with the fp32 blend kept on the FMA
+//                       pipe: byte -> float through the 1.5*2^23 bias trick, truncation through a
+//                       round-toward-zero add, no I2F / F2I (the conversion unit is 1/8 rate on sm_100)
+//   Cutout              the streaming loop plus a box test per octet (augmentations.py:126-144)
+// A per-channel LUT in the program's other slot rides for free: the float table already composes
+// LUT o ToTensor o Normalize; only the fill colour depends on the order of the two ops.
+#pragma once
+
+namespace faa {
+
+constexpr float kBias15 = 12582912.0f;           // 1.5 * 2^23: float(kBias15 + i) is exact for |i| < 2^22
+constexpr uint32_t kBias15Bits = 0x4B400000u;
+
+// byte j (0..3) of w as the float (kBias15 + byte): one PRMT, no conversion instruction
+__device__ __forceinline__ float biased_byte(uint32_t w, int j) {
+    return __uint_as_float(__byte_perm(w, kBias15Bits, 0x7650 + j));      // selector: [7][6][5][j] -> 0x4B40 00 bb
+}
+
+// ---------------------------------------------------------------------------------------------------
+// masked emit: pixels whose bit in `valid` is clear take the fill value pad[ch] (already normalised)
+template <int OUT, bool USE_TAB>
+__device__ __forceinline__ void emit_oct_masked(const AugParams& P, const float* tab, typename OutElem<OUT>::T* o,
+                                                uint32_t plane, const uint32_t px[8], uint32_t valid, const float pad[3]) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        uint32_t u[8]; float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = (px[k] >> (8 * ch)) & 255u;
+        norm8<USE_TAB>(P, tab, ch, u, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ((valid >> k) & 1u) ? v[k] : pad[ch];
+        store_plane8<OUT>(o + ch * plane, v);
+    }
+}
+
+template <int OUT>
+__device__ __forceinline__ void fill_oct(typename OutElem<OUT>::T* o, uint32_t plane, const float pad[3]) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float v[8] = {pad[ch], pad[ch], pad[ch], pad[ch], pad[ch], pad[ch], pad[ch], pad[ch]};
+        store_plane8<OUT>(o + ch * plane, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row-shift geometric ops.  K_SHIFT: source = (x + dx + (x >= bx), y + dy + (y >= by)); K_AFFINE with
+// a0 == a4 == 1.0 and a3 == 0 (ShearX): source = (x + ((a2 + a1*y) >> 16), y) - exact, because the x term
+// of Pillow's fixed-point sum has no fractional bits.
+struct RowShift {
+    int dx, bx, dy, by;       // K_SHIFT
+    int a1, a2;               // ShearX
+    int shear;
+};
+
+__device__ __forceinline__ bool rowshift_of(const OpRec& r, RowShift& rs) {
+    rs.dx = rs.dy = 0; rs.bx = rs.by = 0x7fffffff; rs.a1 = rs.a2 = 0; rs.shear = 0;
+    if (r.kind == K_SHIFT) { rs.dx = r.a[0]; rs.dy = r.a[1]; rs.bx = r.a[2]; rs.by = r.a[3]; return true; }
+    if (r.kind == K_AFFINE && r.a[0] == 65536 && r.a[3] == 0 && r.a[4] == 65536) {
+        rs.shear = 1; rs.a1 = r.a[1]; rs.a2 = r.a[2]; return true;
+    }
+    return false;
+}
+
+// USE_TAB: value = tab[ch][byte] (LUT partner composed with the normalisation, or the exact table);
+// pad[ch]: the normalised fill value for pixels whose source is outside the image
+template <int OUT, bool USE_TAB>
+__device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
+                                                    const RowShift rs, int flip, void* out_img, int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const int W = P.W, H = P.H;
+    const uint32_t opr = (uint32_t)W >> 3;
+    const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
+    const uint32_t plane = (uint32_t)H * (uint32_t)W, pitch = (uint32_t)W * 3u;
+    const uint32_t s_len = c.s_len2 ? c.s_len2 + 2u : 0u;
+    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    FastDiv dq; dq.init(opr, P.rcp_opr);
+    uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
+    const uint32_t dr = dq.div(blockDim.x), dxo = blockDim.x - dr * opr;
+    for (uint32_t i = threadIdx.x; i < n8; i += blockDim.x) {
+        const int y = oy0 + (int)r;
+        const int ax0 = flip ? W - 8 - (int)ox * 8 : (int)ox * 8;        // first column of the octet in the augmented image
+        const int ys = rs.shear ? y : y + rs.dy + (y >= rs.by);
+        const int s0 = rs.shear ? (rs.a2 + rs.a1 * y) >> 16 : rs.dx + (ax0 >= rs.bx);
+        const int s7 = rs.shear ? s0 : rs.dx + (ax0 + 7 >= rs.bx);
+        const int sx0 = ax0 + s0;
+        T* o = dst + 8u * i;
+        if ((unsigned)ys >= (unsigned)H || sx0 + 7 + (s7 - s0) < 0 || sx0 >= W) {
+            fill_oct<OUT>(o, plane, pad);                                 // nothing of the octet has a source
+        } else if (s0 == s7 && sx0 >= 0 && sx0 + 7 < W) {
+            // all eight sources exist: 24 contiguous bytes from byte B0 of the image
+            const uint32_t B0 = (uint32_t)ys * pitch + (uint32_t)sx0 * 3u, k = B0 & 3u, A = B0 - k;
+            const uint32_t rel = A - c.s_lo;
+            uint32_t v[7];
+            if (rel <= s_len - 28u && s_len >= 28u) {                     // aligned words [A, A+28) are staged
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(c.sraw + rel);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = p[j];
+                v[6] = k ? p[6] : 0u;
+            } else {
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(c.raw + A);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = __ldg(p + j);
+                v[6] = k ? __ldg(p + 6) : 0u;                             // never past the image: only read when it holds a source byte
+            }
+            uint32_t w[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) w[j] = __funnelshift_r(v[j], v[j + 1], 8u * k);
+            if (flip) stream_oct<OUT, USE_TAB, true>(P, w, tab, o, plane);
+            else stream_oct<OUT, USE_TAB, false>(P, w, tab, o, plane);
+        } else {
+            // row edge or a shift break inside the octet: per pixel
+            uint32_t px[8]; uint32_t valid = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int x = flip ? ax0 + 7 - j : ax0 + j;              // output pixel j of the octet
+                const int xs = x + (rs.shear ? s0 : rs.dx + (x >= rs.bx));
+                const bool ok = (unsigned)xs < (unsigned)W;
+                px[j] = ok ? load_raw(c, xs, ys) : 0u;
+                valid |= (uint32_t)ok << j;
+            }
+            emit_oct_masked<OUT, USE_TAB>(P, tab, o, plane, px, valid, pad);
+        }
+        ox += dxo; r += dr;
+        if (ox >= opr) { ox -= opr; ++r; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// General affine gather (ShearY, Rotate): one quad per thread and iteration, sources from global memory.
+template <int OUT, bool USE_TAB>
+__device__ __forceinline__ void final_rows_affine(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
+                                                  const OpRec op, int flip, void* out_img, int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const int W = P.W, H = P.H;
+    const uint32_t qpr = (uint32_t)W >> 2;
+    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
+    const uint32_t plane = (uint32_t)H * (uint32_t)W;
+    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    FastDiv dq; dq.init(qpr, P.rcp_wq);
+    uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
+    const uint32_t dr = dq.div(blockDim.x), dxq = blockDim.x - dr * qpr;
+    const int a0 = op.a[0], a1 = op.a[1], a2 = op.a[2], a3 = op.a[3], a4 = op.a[4], a5 = op.a[5];
+    const int dfx = flip ? -a0 : a0, dfy = flip ? -a3 : a3;
+    const uint8_t* raw = c.raw;
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int y = oy0 + (int)r;
+        const int ax0 = flip ? W - 1 - (int)qx * 4 : (int)qx * 4;
+        int fx = a2 + a0 * ax0 + a1 * y, fy = a5 + a3 * ax0 + a4 * y;
+        uint32_t b[4][3]; uint32_t valid = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                                    // twelve byte loads, no branch in between
+            const int xs = fx >> 16, ys = fy >> 16;
+            const bool ok = (unsigned)xs < (unsigned)W && (unsigned)ys < (unsigned)H;
+            const uint8_t* p = raw + (ok ? (uint32_t)(ys * W + xs) * 3u : 0u);
+            b[k][0] = __ldg(p); b[k][1] = __ldg(p + 1); b[k][2] = __ldg(p + 2);
+            valid |= (uint32_t)ok << k;
+            fx += dfx; fy += dfy;
+        }
+        T* o = dst + 4u * q;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float v[4];
+            if (USE_TAB) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = tab[ch * 256 + b[k][ch]];
+            } else {
+                const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
+                const float2 r0 = __ffma2_rn(make_float2((float)b[0][ch], (float)b[1][ch]), sc, bi);
+                const float2 r1 = __ffma2_rn(make_float2((float)b[2][ch], (float)b[3][ch]), sc, bi);
+                v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
+            }
+            if (valid != 15u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = ((valid >> k) & 1u) ? v[k] : pad[ch];
+            }
+            store_plane4<OUT>(o + ch * plane, v, true, 4);
+        }
+        qx += dxq; r += dr;
+        if (qx >= qpr) { qx -= qpr; ++r; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ImageEnhance.Color alone: out = blend(luma, px, alpha) per channel, then ToTensor + Normalize.
+// The blend (Pillow Blend.c: fp32, separate multiply and add, truncation, clip when alpha is outside
+// [0,1]) is evaluated on biased floats: fb = kBias15 + byte (exact), px - luma = fb_px - fb_l (exact),
+// t = l + alpha * (px - l) with the reference's two roundings, trunc(t) = (t +rz kBias15) - kBias15 for
+// t >= 0 and anything below zero clamps to zero either way.
+template <int OUT, bool TAB, bool CLIP>
+__device__ __forceinline__ void final_rows_color(const AugParams& P, const float* s_norm, const Ctx& c, float alpha, int flip,
+                                                 void* out_img, int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const int W = P.W;
+    const uint32_t opr = (uint32_t)W >> 3;
+    const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
+    const uint32_t plane = (uint32_t)P.H * (uint32_t)W;
+    const uint8_t* src = c.sraw + ((uint32_t)oy0 * (uint32_t)W * 3u - c.s_lo);
+    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    FastDiv dq; dq.init(opr, P.rcp_opr);
+    uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
+    const uint32_t dr = dq.div(blockDim.x), dxo = blockDim.x - dr * opr;
+    for (uint32_t i = threadIdx.x; i < n8; i += blockDim.x) {
+        const uint32_t sox = flip ? opr - 1u - ox : ox;
+        const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * (r * opr + sox));
+        const uint2 wa = s8[0], wb = s8[1], wc = s8[2];
+        const uint32_t w[6] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y};
+        float v[3][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int sk = flip ? 7 - k : k;                              // source pixel of output pixel k
+            float fb[3]; uint32_t u[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int bidx = 3 * sk + ch;
+                fb[ch] = biased_byte(w[bidx >> 2], bidx & 3);
+                u[ch] = (w[bidx >> 2] >> (8 * (bidx & 3))) & 255u;
+            }
+            const uint32_t l = (19595u * u[0] + 38470u * u[1] + 7471u * u[2] + 0x8000u) >> 16;      // Pillow rgb2l
+            const float fl = __uint_as_float(kBias15Bits + l);           // kBias15 + l
+            const float lf = __fadd_rn(fl, -kBias15);                    // (float)l
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float d = __fadd_rn(fb[ch], -fl);                  // (float)(px - l), exact
+                const float t = __fadd_rn(lf, __fmul_rn(alpha, d));      // Blend.c, no contraction
+                float z = __fadd_rz(t, kBias15);                         // kBias15 + floor(t)
+                if (CLIP) z = fminf(fmaxf(z, kBias15), kBias15 + 255.0f);
+                v[ch][k] = __fadd_rn(z, -kBias15);                       // the byte value as a float, exact
+            }
+        }
+        T* o = dst + 8u * i;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float nv[8];
+            if (TAB) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nv[k] = s_norm[ch * 256 + (int)v[ch][k]];
+            } else {
+                const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    const float2 rr = __ffma2_rn(make_float2(v[ch][k], v[ch][k + 1]), sc, bi);
+                    nv[k] = rr.x; nv[k + 1] = rr.y;
+                }
+            }
+            store_plane8<OUT>(o + ch * plane, nv);
+        }
+        ox += dxo; r += dr;
+        if (ox >= opr) { ox -= opr; ++r; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cutout alone: the streaming loop, except for octets that touch the (clipped, inclusive) box
+template <int OUT, bool TAB>
+__device__ __forceinline__ void final_rows_cutout(const AugParams& P, const float* s_norm, const Ctx& c, const Box bx, int flip,
+                                                  void* out_img, int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const int W = P.W;
+    const uint32_t opr = (uint32_t)W >> 3;
+    const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
+    const uint32_t plane = (uint32_t)P.H * (uint32_t)W;
+    const uint8_t* src = c.sraw + ((uint32_t)oy0 * (uint32_t)W * 3u - c.s_lo);
+    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    FastDiv dq; dq.init(opr, P.rcp_opr);
+    uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
+    const uint32_t dr = dq.div(blockDim.x), dxo = blockDim.x - dr * opr;
+    for (uint32_t i = threadIdx.x; i < n8; i += blockDim.x) {
+        const int y = oy0 + (int)r;
+        const uint32_t sox = flip ? opr - 1u - ox : ox;
+        const int sx0 = (int)sox * 8;                                     // first source column of the octet
+        const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * (r * opr + sox));
+        const uint2 wa = s8[0], wb = s8[1], wc = s8[2];
+        const uint32_t w[6] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y};
+        T* o = dst + 8u * i;
+        if (y < bx.y0 || y > bx.y1 || sx0 + 7 < bx.x0 || sx0 > bx.x1) {
+            if (flip) stream_oct<OUT, TAB, true>(P, w, s_norm, o, plane);
+            else stream_oct<OUT, TAB, false>(P, w, s_norm, o, plane);
+        } else {
+            uint32_t q[8], px[8];
+            unpack12(w[0], w[1], w[2], q); unpack12(w[3], w[4], w[5], q + 4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int sk = flip ? 7 - k : k;
+                const int x = sx0 + sk;
+                px[k] = (x >= bx.x0 && x <= bx.x1) ? kCutoutRGB : q[sk];
+            }
+            emit_oct<OUT, TAB>(P, s_norm, o, plane, px);
+        }
+        ox += dxo; r += dr;
+        if (ox >= opr) { ox -= opr; ++r; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sharpness (ImageEnhance.Sharpness = blend(img.filter(SMOOTH), img, alpha), augmentations.py:112-114) as a
+// filter on the BYTE STREAM: with interleaved RGB the horizontal neighbours of byte k are bytes k-3 and k+3, so
+// the 3x3 SMOOTH sum needs no channel bookkeeping:
+//     col[k] = a[k] + b[k] + c[k]                    (rows y-1, y, y+1)
+//     S[k]   = col[k-3] + col[k] + col[k+3] + 4 b[k]   ([1 1 1; 1 5 1; 1 1 1])
+//     deg[k] = (2 S[k] + 13) / 26                     (/13, rounded half up)
+// Bytes travel as 16-bit lanes, two per register, in stream order: a 3-byte shift of the stream is ONE PRMT.
+// The division and the fp32 blend run on the FMA pipe (biased floats, see final_rows_color); no I2F / F2I.
+// One quad (12 output bytes) per thread and iteration; `tab` as in the streaming loop.
+__device__ __forceinline__ uint32_t pair_lo(uint32_t w) { return __byte_perm(w, 0u, 0x4140); }   // (b0, b1) as 16-bit lanes
+__device__ __forceinline__ uint32_t pair_hi(uint32_t w) { return __byte_perm(w, 0u, 0x4342); }   // (b2, b3)
+
+template <int OUT, bool USE_TAB, bool CLIP>
+__device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const float* tab, const Ctx& c, float alpha, int flip,
+                                                  void* out_img, int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const int W = P.W, H = P.H;
+    const uint32_t qpr = (uint32_t)W >> 2;
+    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
+    const uint32_t plane = (uint32_t)H * (uint32_t)W, pitch = (uint32_t)W * 3u;
+    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    FastDiv dq; dq.init(qpr, P.rcp_wq);
+    uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
+    const uint32_t dr = dq.div(blockDim.x), dxq = blockDim.x - dr * qpr;
+    const float k26 = 1.0f / 26.0f, h26 = 0.5f / 26.0f;
+    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int y = oy0 + (int)r;
+        const uint32_t sqx = flip ? qpr - 1u - qx : qx;                   // source quad of this output quad
+        const uint32_t* rb = reinterpret_cast<const uint32_t*>(c.sraw + ((uint32_t)y * pitch + 12u * sqx - c.s_lo));
+        float zb[12];                                                    // kBias15 + output byte, source order
+        if (y == 0 || y == H - 1) {                                      // border rows are copied (Pillow filter)
+#pragma unroll
+            for (int k = 0; k < 12; ++k) zb[k] = biased_byte(rb[k >> 2], k & 3);
+        } else {
+            const uint32_t* ra = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(rb) - pitch);
+            const uint32_t* rc = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(rb) + pitch);
+            const bool has_l = sqx > 0u, has_r = sqx + 1u < qpr;
+            // words [-1 .. 3] of the three rows: bytes -4 .. 15 relative to the quad's first byte
+            uint32_t wb[5], colp[10], ctr[10];
+            {
+                uint32_t wa[5], wc[5];
+                wa[0] = has_l ? ra[-1] : 0u; wb[0] = has_l ? rb[-1] : 0u; wc[0] = has_l ? rc[-1] : 0u;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) { wa[j] = ra[j - 1]; wb[j] = rb[j - 1]; wc[j] = rc[j - 1]; }
+                wa[4] = has_r ? ra[3] : 0u; wb[4] = has_r ? rb[3] : 0u; wc[4] = has_r ? rc[3] : 0u;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {                             // pair m covers bytes 2m, 2m+1 (from byte -4)
+                    ctr[2 * j] = pair_lo(wb[j]); ctr[2 * j + 1] = pair_hi(wb[j]);
+                    colp[2 * j] = pair_lo(wa[j]) + ctr[2 * j] + pair_lo(wc[j]);
+                    colp[2 * j + 1] = pair_hi(wa[j]) + ctr[2 * j + 1] + pair_hi(wc[j]);
+                }
+            }
+            uint32_t sh[9];                                              // sh[m] = stream shifted by 3 bytes: (col[2m-3], col[2m-2])
+#pragma unroll
+            for (int m = 2; m <= 10; ++m) sh[m - 2] = m < 10 ? __byte_perm(colp[m - 2], colp[m - 1], 0x5432)
+                                                             : __byte_perm(colp[8], colp[9], 0x5432);
+#pragma unroll
+            for (int m = 2; m < 8; ++m) {                                 // output bytes 2m-4, 2m-3
+                const uint32_t t = sh[m - 2] + colp[m] + sh[m + 1];      // col[k-3] + col[k] + col[k+3]
+                const uint32_t x2 = 2u * t + 8u * ctr[m] + 0x000D000Du;  // 2 S + 13 per lane (< 6644)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = 2 * m + h;                             // byte index from byte -4
+                    const float fx = __uint_as_float(__byte_perm(x2, kBias15Bits, h ? 0x7632 : 0x7610));    // kBias15 + (2S+13)
+                    const float u = fmaf(__fadd_rn(fx, -kBias15), k26, h26);        // (2S+13+.5)/26: never within 0.019 of an integer
+                    const float fdeg = __fadd_rz(u, kBias15);                       // kBias15 + floor(u)
+                    const float fctr = biased_byte(wb[k >> 2], k & 3);
+                    const float d = __fadd_rn(fctr, -fdeg);                         // (float)(px - deg), exact
+                    const float tt = __fadd_rn(__fadd_rn(fdeg, -kBias15), __fmul_rn(alpha, d));   // Blend.c
+                    float z = __fadd_rz(tt, kBias15);
+                    if (CLIP) z = fminf(fmaxf(z, kBias15), kBias15 + 255.0f);
+                    zb[k - 4] = z;
+                }
+            }
+            // first / last pixel of the row are image border: copied
+            if (!has_l) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) zb[k] = biased_byte(wb[1], k);
+            }
+            if (!has_r) {
+#pragma unroll
+                for (int k = 9; k < 12; ++k) zb[k] = biased_byte(wb[3], k - 8);
+            }
+        }
+        T* o = dst + 4u * q;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float zz = zb[3 * k + ch];
+                v[k] = USE_TAB ? tab[ch * 256 + (__float_as_uint(zz) & 255u)] : __fadd_rn(zz, -kBias15);
+            }
+            if (flip) { float t0 = v[0], t1 = v[1]; v[0] = v[3]; v[1] = v[2]; v[2] = t1; v[3] = t0; }
+            if (!USE_TAB) {
+                const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
+                const float2 r0 = __ffma2_rn(make_float2(v[0], v[1]), sc, bi), r1 = __ffma2_rn(make_float2(v[2], v[3]), sc, bi);
+                v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
+            }
+            store_plane4<OUT>(o + ch * plane, v, true, 4);
+        }
+        qx += dxq; r += dr;
+        if (qx >= qpr) { qx -= qpr; ++r; }
+    }
+}
+
+}  // namespace faa

@@ -41,6 +41,7 @@ namespace cg = cooperative_groups;
 namespace faa {
 
 constexpr int kThreads = 256;
+constexpr int kMaxDevices = 64;
 #ifndef FAA_MIN_CTAS
 #define FAA_MIN_CTAS 4
 #endif
@@ -54,6 +55,10 @@ struct __align__(16) ImgState {
     uint8_t lutc[768];          // composed LUT (C_LUT programs)
     HistPart parts[3][32];
     unsigned long long suml[2]; // per-slot local partial luma sums
+    uint32_t xpart[8];          // scalar statistics of this CTA's band (read remotely through DSMEM): per-channel
+                                // min [0..2], max [3..5] (AutoContrast) or the luma sum [6] lo, [7] hi (Contrast)
+    uint32_t xtot[8];           // ... reduced over the cluster
+    uint32_t wred[8][8];        // per-warp partials
 };
 
 struct FastDiv {
@@ -104,7 +109,13 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
         if (P.boxes_out != nullptr)
             for (int j = 0; j < P.n_op; ++j) P.boxes_out[(size_t)i * P.n_op + j] = bx[j];
     }
-    if (P.order == nullptr || P.progs == nullptr) return;
+    if (P.order == nullptr || P.progs == nullptr) {
+        if (P.ready != nullptr) {
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.ready), "r"(P.ticket) : "memory"); }
+        }
+        return;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -117,6 +128,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {        // scheduling order only: any order is correct
         const int b = P.progs[P.first + t].bucket;
         P.order[P.first + s_base[b] + atomicAdd(&s_count[b], 1)] = t;
+    }
+    if (P.ready != nullptr) {                                    // chained steps: the pixel kernels poll this word
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.ready), "r"(P.ticket) : "memory"); }
     }
 }
 
@@ -142,6 +157,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(b), "r"(phase) : "memory");
     }
+}
+
+// chained steps: programs / order / n_heavy of this step are complete once *ready == ticket (written with
+// release semantics by the resolve kernel, which precedes this kernel in its stream and has therefore started)
+__device__ __forceinline__ void wait_ticket(const int32_t* ready, int32_t ticket) {
+    if (ready == nullptr) return;
+    if (threadIdx.x == 0) {
+        int32_t v;
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory"); } while (v != ticket);
+    }
+    __syncthreads();
 }
 
 // the byte range of image rows a CTA may touch through the band-local paths
@@ -752,6 +778,112 @@ __device__ __forceinline__ void final_rows_stream(const AugParams& P, const floa
     }
 }
 
+// ---- octet (8-pixel) streaming: W % 8 == 0, output size == image size, no crop --------------------
+// Eight consecutive pixels of one row are 24 contiguous, 8-byte aligned bytes; each plane gets ONE 16-byte
+// store (fp16 / bf16) and the normalisation runs as packed fp32x2 fused multiply-adds (sm_100 FFMA2).
+template <int OUT>
+__device__ __forceinline__ void store_plane8(typename OutElem<OUT>::T* o, const float v[8]) {
+    if constexpr (OUT == OUT_F32) {
+        reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (OUT == OUT_F16) {
+        __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+        uint4 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint4*>(o) = u;
+    } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+        uint4 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint4*>(o) = u;
+    }
+}
+
+// normalised values of one plane from eight byte values: table lookups, or packed fma
+template <bool USE_TAB>
+__device__ __forceinline__ void norm8(const AugParams& P, const float* tab, int ch, const uint32_t u[8], float v[8]) {
+    if (USE_TAB) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tab[ch * 256 + u[k]];
+    } else {
+        const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const float2 r = __ffma2_rn(make_float2((float)u[k], (float)u[k + 1]), sc, bi);
+            v[k] = r.x; v[k + 1] = r.y;
+        }
+    }
+}
+
+// w[6]: the 24 source bytes of the octet in memory order; FLIP reverses the pixel order
+template <int OUT, bool USE_TAB, bool FLIP>
+__device__ __forceinline__ void stream_oct(const AugParams& P, const uint32_t w[6], const float* tab,
+                                           typename OutElem<OUT>::T* o, uint32_t plane) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        uint32_t u[8]; float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int b = 3 * (FLIP ? 7 - k : k) + ch;                  // which of the 24 bytes
+            u[k] = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+        }
+        norm8<USE_TAB>(P, tab, ch, u, v);
+        store_plane8<OUT>(o + ch * plane, v);
+    }
+}
+
+// px[8]: eight 24-bit pixels already in OUTPUT order
+template <int OUT, bool TAB>
+__device__ __forceinline__ void emit_oct(const AugParams& P, const float* s_norm, typename OutElem<OUT>::T* o, uint32_t plane,
+                                         const uint32_t px[8]) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        uint32_t u[8]; float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = (px[k] >> (8 * ch)) & 255u;
+        norm8<TAB>(P, s_norm, ch, u, v);
+        store_plane8<OUT>(o + ch * plane, v);
+    }
+}
+
+// the launch geometry allows octets: W % 8 == 0 and the output is the (possibly mirrored) image itself
+__device__ __forceinline__ bool octet_geometry(const AugParams& P, const TailInfo& t) {
+    return P.octets != 0 && t.crop_dx == 0 && t.crop_dy == 0;      // P.octets: W % 8 == 0, out size == image size, 16-byte aligned output
+}
+
+template <int OUT, bool USE_TAB, bool FLIP>
+__device__ __forceinline__ void final_rows_stream8(const AugParams& P, const float* tab, const Ctx& c, void* out_img,
+                                                   int oy0, int oy1) {
+    using T = typename OutElem<OUT>::T;
+    const uint32_t opr = (uint32_t)P.W >> 3;                      // octets per row
+    const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
+    const uint32_t plane = (uint32_t)P.H * (uint32_t)P.W;
+    const uint8_t* src = c.sraw + ((uint32_t)oy0 * (uint32_t)P.W * 3u - c.s_lo);   // first byte of row oy0 (staged)
+    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)P.W;
+    if (!FLIP) {                                                  // source and output both advance linearly
+        for (uint32_t i = threadIdx.x; i < n8; i += blockDim.x) {
+            const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * i);
+            const uint2 a = s8[0], b = s8[1], d = s8[2];
+            const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
+            stream_oct<OUT, USE_TAB, false>(P, w, tab, dst + 8u * i, plane);
+        }
+    } else {
+        FastDiv dq; dq.init(opr, P.rcp_opr);
+        uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
+        const uint32_t dr = dq.div(blockDim.x), dx = blockDim.x - dr * opr;
+        for (uint32_t i = threadIdx.x; i < n8; i += blockDim.x) {
+            const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * (r * opr + (opr - 1u - ox)));
+            const uint2 a = s8[0], b = s8[1], d = s8[2];
+            const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
+            stream_oct<OUT, USE_TAB, true>(P, w, tab, dst + 8u * i, plane);
+            ox += dx; r += dr;
+            if (ox >= opr) { ox -= opr; ++r; }
+        }
+    }
+}
+
 // PLAIN / LUT final pass: the streaming loop when possible, else the generic aligned loop.
 // `ftab` (768 floats) is only read for LUT programs and must hold normalise(ch, lutc[ch][b]).
 template <int OUT, bool TAB, bool LUT>
@@ -759,6 +891,16 @@ __device__ __forceinline__ void final_rows_plain_lut(const AugParams& P, const f
                                                      const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1) {
     if constexpr (OUT != OUT_U8_HWC) {
         if ((!LUT || ftab != nullptr) && band_fully_staged(c, t, oy0, oy1)) {
+            if (octet_geometry(P, t)) {
+                if (t.flip) {
+                    if (LUT) final_rows_stream8<OUT, true, true>(P, ftab, c, out_img, oy0, oy1);
+                    else final_rows_stream8<OUT, TAB, true>(P, s_norm, c, out_img, oy0, oy1);
+                } else {
+                    if (LUT) final_rows_stream8<OUT, true, false>(P, ftab, c, out_img, oy0, oy1);
+                    else final_rows_stream8<OUT, TAB, false>(P, s_norm, c, out_img, oy0, oy1);
+                }
+                return;
+            }
             const float pad[3] = {normalise<TAB>(P, s_norm, 0, 0u), normalise<TAB>(P, s_norm, 1, 0u), normalise<TAB>(P, s_norm, 2, 0u)};
             if (LUT) final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
             else final_rows_stream<OUT, TAB>(P, s_norm, pad, c, t, out_img, oy0, oy1);
@@ -981,6 +1123,131 @@ __device__ void final_pass_mix(const AugParams& P, const float* s_norm, const Im
     }
 }
 
+}  // namespace faa
+#include "faa_fast.cuh"
+namespace faa {
+
+// ---- scalar statistics: AutoContrast needs only per-channel min / max, Contrast only the luma sum ----------
+// (PIL ImageOps.autocontrast with cutoff 0 uses the first / last non-zero histogram bin, augmentations.py:64-65;
+//  ImageEnhance.Contrast the rounded mean luma, :97-99.)  For programs "statistics op [+ static per-channel LUT]"
+// the band is scanned with packed 16-bit min / max (VIMNMX3.U16x2) or a luma sum - no shared-memory atomics -,
+// the per-band scalars (32 bytes) are exchanged with ONE cluster barrier and every CTA builds the float table
+// tab[ch][b] = normalise(lut1(lut0(b))) directly.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool scalar_stats_program(const Prog& g) {
+    const int k0 = g.op[0].kind, k1 = g.op[1].kind;
+    return g.cls == C_LUT && (k0 == K_AUTOCONTRAST || k0 == K_CONTRAST) &&
+           (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
+}
+
+// returns with ftab / st.lutc complete (barrier included); the caller must call cluster_wait() once more before
+// the CTA exits when `bands > 1` (peers may still be reading this CTA's record)
+template <bool TAB>
+__device__ void build_scalar_stats_table(const AugParams& P, const float* s_norm, ImgState& st, const Ctx& c, int y0, int y1,
+                                         cg::cluster_group& cluster, float* ftab) {
+    const int k0 = st.prog.op[0].kind;
+    const bool ac = k0 == K_AUTOCONTRAST;
+    const uint32_t nq = (uint32_t)(y1 - y0) * (uint32_t)P.W / 4u;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(c.sraw + ((uint32_t)y0 * (uint32_t)P.W * 3u - c.s_lo));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ac) {
+        // quad = 12 bytes R G B R | G B R G | B R G B: even / odd bytes of each word as 16-bit lanes
+        uint32_t mnA = 0x00FF00FFu, mnB = 0x00FF00FFu, mnC = 0x00FF00FFu, mxA = 0u, mxB = 0u, mxC = 0u;   // lanes (R,B) (G,R) (B,G)
+        for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
+            const uint32_t w0 = src[3u * i], w1 = src[3u * i + 1u], w2 = src[3u * i + 2u];
+            const uint32_t e0 = __byte_perm(w0, 0u, 0x4240), o0 = __byte_perm(w0, 0u, 0x4341);
+            const uint32_t e1 = __byte_perm(w1, 0u, 0x4240), o1 = __byte_perm(w1, 0u, 0x4341);
+            const uint32_t e2 = __byte_perm(w2, 0u, 0x4240), o2 = __byte_perm(w2, 0u, 0x4341);
+            mnA = __vimin3_u16x2(mnA, e0, o2); mxA = __vimax3_u16x2(mxA, e0, o2);
+            mnB = __vimin3_u16x2(mnB, o0, e1); mxB = __vimax3_u16x2(mxB, o0, e1);
+            mnC = __vimin3_u16x2(mnC, o1, e2); mxC = __vimax3_u16x2(mxC, o1, e2);
+        }
+        uint32_t v[6];
+        v[0] = min(mnA & 0xFFFFu, mnB >> 16); v[1] = min(mnB & 0xFFFFu, mnC >> 16); v[2] = min(mnA >> 16, mnC & 0xFFFFu);
+        v[3] = max(mxA & 0xFFFFu, mxB >> 16); v[4] = max(mxB & 0xFFFFu, mxC >> 16); v[5] = max(mxA >> 16, mxC & 0xFFFFu);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { v[j] = __reduce_min_sync(0xffffffffu, v[j]); v[3 + j] = __reduce_max_sync(0xffffffffu, v[3 + j]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) st.wred[warp][j] = v[j];
+        }
+    } else {
+        uint32_t local = 0;
+        for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
+            uint32_t q[4];
+            unpack12(src[3u * i], src[3u * i + 1u], src[3u * i + 2u], q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) local += luma_of(q[k]);
+        }
+        local = __reduce_add_sync(0xffffffffu, local);                     // < 2^32: a warp covers < 2^24 pixels of a band
+        if (lane == 0) st.wred[warp][6] = local;
+    }
+    __syncthreads();
+    const int nwarp = (int)(blockDim.x >> 5);
+    if (threadIdx.x < 8) {
+        const int j = threadIdx.x;
+        if (ac) {
+            uint32_t r = j < 3 ? 255u : 0u;
+            if (j < 6) for (int w = 0; w < nwarp; ++w) r = j < 3 ? min(r, st.wred[w][j]) : max(r, st.wred[w][j]);
+            st.xpart[j] = r;
+        } else if (j == 6) {
+            unsigned long long t = 0;
+            for (int w = 0; w < nwarp; ++w) t += st.wred[w][6];
+            st.xpart[6] = (uint32_t)t; st.xpart[7] = (uint32_t)(t >> 32);
+        }
+    }
+    const int bands = P.bands;
+    if (bands > 1) { cluster_arrive(); cluster_wait(); } else __syncthreads();       // every band's record is complete
+    if (threadIdx.x < 8) {
+        const int j = threadIdx.x;
+        uint32_t v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)                                        // remote loads in flight together
+            v[r] = r < bands ? (bands > 1 ? cluster.map_shared_rank(&st.xpart[0], r)[j] : st.xpart[j]) : (j < 3 ? 255u : 0u);
+        uint32_t t;
+        if (j < 3) t = min(min(min(v[0], v[1]), min(v[2], v[3])), min(min(v[4], v[5]), min(v[6], v[7])));
+        else if (j < 6) t = max(max(max(v[0], v[1]), max(v[2], v[3])), max(max(v[4], v[5]), max(v[6], v[7])));
+        else t = 0u;
+        st.xtot[j] = t;
+        if (j == 6) {                                                      // 64-bit luma total
+            unsigned long long tot = 0;
+            for (int r = 0; r < bands; ++r) {
+                const uint32_t* xp = bands > 1 ? cluster.map_shared_rank(&st.xpart[0], r) : &st.xpart[0];
+                tot += (unsigned long long)xp[6] | ((unsigned long long)xp[7] << 32);
+            }
+            st.xtot[6] = (uint32_t)tot; st.xtot[7] = (uint32_t)(tot >> 32);
+        }
+    }
+    __syncthreads();
+    if (bands > 1) cluster_arrive();                                       // this CTA is done reading its peers
+    // the table: entry i of channel ch by thread i (blockDim.x == 256)
+    const OpRec o0 = st.prog.op[0], o1 = st.prog.op[1];
+    const uint32_t n_pixels = (uint32_t)P.H * (uint32_t)P.W;
+    const uint32_t mean = ac ? 0u : contrast_mean((unsigned long long)st.xtot[6] | ((unsigned long long)st.xtot[7] << 32), n_pixels);
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int ch = i >> 8, ix = i & 255;
+        uint32_t v;
+        if (ac) {                                                          // == hist_lut_lane(K_AUTOCONTRAST)
+            const int lo = (int)st.xtot[ch], hi = (int)st.xtot[3 + ch];
+            if (hi <= lo) v = (uint32_t)ix;
+            else {
+                const double scale = 255.0 / (double)(hi - lo);
+                const double offset = d_mul(-(double)lo, scale);
+                const int t = (int)d_add(d_mul((double)ix, scale), offset);
+                v = (uint32_t)(t < 0 ? 0 : t > 255 ? 255 : t);
+            }
+        } else {
+            v = lut_entry_static(o0, (uint32_t)ix, mean);
+        }
+        if (o1.kind != K_NONE) v = lut_entry_static(o1, v, 0u);
+        st.lutc[i] = (uint8_t)v;
+        ftab[i] = normalise<TAB>(P, s_norm, ch, v);
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------
 // launch 2
 template <int OUT, int NSRC, bool TAB>
@@ -999,12 +1266,13 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
 
     // Programmatic dependent launch: everything above overlaps the resolve kernel's tail; the
     // schedule and the programs it writes are only read after this point.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!P.chain) asm volatile("griddepcontrol.wait;" ::: "memory");
+    wait_ticket(P.ready, P.ticket);
 
     // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule
-    if (P.n_heavy != nullptr && (int)blockIdx.y >= *P.n_heavy) return;      // cluster-uniform
+    if (P.n_heavy != nullptr && (int)blockIdx.y >= __ldcg(P.n_heavy)) return;      // cluster-uniform
     // LPT schedule entry: a uniform load per warp (no shared-memory hand-off, no barrier)
-    const int img = P.order ? __ldg(P.order + P.first + blockIdx.y) : (int)blockIdx.y;
+    const int img = P.order ? __ldcg(P.order + P.first + blockIdx.y) : (int)blockIdx.y;
     int src_idx[NSRC];
     src_idx[0] = P.first + img;
     if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
@@ -1020,8 +1288,12 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     for (int s = 0; s < NSRC; ++s)
         if (threadIdx.x < sizeof(Prog) / 4)
             reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
-                __ldg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
+                __ldcg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
     __syncthreads();
+    // chained steps: the next kernel of the stream may start once every CTA of this one has copied its program
+    // (it may overwrite the OTHER program slot only); Sharpness->gather programs also own a scratch image that
+    // the next step reuses, so they only release at exit
+    if (P.chain && st[0].prog.cls != C_SG) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
@@ -1052,14 +1324,45 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
             cg2.op[0] = c.op[1]; cg2.box[0] = c.box[1]; cg2.op[1].kind = K_NONE;
             final_rows_cls<OUT, TAB>(C_SG, P, s_norm, cg2, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
         } else {
-            any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
-            // LUT programs: composed LUT o normalisation table in the (now idle) slot-0 histogram
             float* ftab = nullptr;
-            if (OUT != OUT_U8_HWC && cls == C_LUT) {
+            bool peers_pending = false;
+            const TailInfo t0 = make_tail(P, st[0].prog);
+            if (OUT != OUT_U8_HWC && (P.W & 3) == 0 && scalar_stats_program(st[0].prog) && P.stage &&
+                band_fully_staged(c, TailInfo{0, 0, 0, 0, 0, 0, 0}, y0, y1)) {
+                // AutoContrast / Contrast [+ static LUT]: min / max or luma sum, one cluster barrier, direct table
                 ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
-                build_ftab<TAB>(P, s_norm, st[0].lutc, ftab);
+                build_scalar_stats_table<TAB>(P, s_norm, st[0], c, y0, y1, cluster, ftab);
+                peers_pending = P.bands > 1;
+            } else {
+                any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
+                // LUT programs: composed LUT o normalisation table in the (now idle) slot-0 histogram
+                if (OUT != OUT_U8_HWC && cls == C_LUT) {
+                    ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
+                    build_ftab<TAB>(P, s_norm, st[0].lutc, ftab);
+                }
             }
-            final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1, ftab);
+            bool done = false;
+            if constexpr (OUT != OUT_U8_HWC) {
+                const int k1 = st[0].prog.op[1].kind;
+                if (cls == C_SHARP && octet_geometry(P, t0) && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS) &&
+                    band_fully_staged(c, t0, max(oy0 - 1, 0), min(oy1 + 1, P.H))) {
+                    // Sharpness [+ static LUT]: byte-stream 3x3 (faa_fast.cuh); the partner LUT rides in the float table
+                    const float alpha = bits_to_float(st[0].prog.op[0].a[0]);
+                    const bool clip = st[0].prog.op[0].a[1] != 0;
+                    if (k1 != K_NONE) {
+                        ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
+                        build_ftab<TAB>(P, s_norm, st[0].lut[1], ftab);     // (prepare_image built the static LUT of slot 1)
+                        if (clip) final_rows_sharp4<OUT, true, true>(P, ftab, c, alpha, t0.flip, out_img, oy0, oy1);
+                        else final_rows_sharp4<OUT, true, false>(P, ftab, c, alpha, t0.flip, out_img, oy0, oy1);
+                    } else {
+                        if (clip) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t0.flip, out_img, oy0, oy1);
+                        else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t0.flip, out_img, oy0, oy1);
+                    }
+                    done = true;
+                }
+            }
+            if (!done) final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, t0, out_img, oy0, oy1, ftab);
+            if (peers_pending) cluster_wait();                             // peers have read this CTA's statistics record
         }
         zero_box_rows<OUT>(P, st[0].prog, out_img, oy0, oy1);
     } else {
@@ -1096,14 +1399,16 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     const uint32_t s_lo = P.geo[1].lo[band], s_len = P.geo[1].len[band];
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
-    const int n_heavy = *P.n_heavy;
+    wait_ticket(P.ready, P.ticket);
+    const int n_heavy = __ldcg(P.n_heavy);
     if ((int)blockIdx.y >= P.B - n_heavy) return;
-    const int img = __ldg(P.order + P.first + n_heavy + blockIdx.y);     // uniform load per warp
+    const int img = __ldcg(P.order + P.first + n_heavy + blockIdx.y);     // uniform load per warp
     const int idx = P.first + img;
     if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)idx * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
-        reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
+        reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
     __syncthreads();
+    if (P.chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied: see the cluster kernel
     const uint32_t lut_mask = s_prog.lut_mask;
     if (lut_mask) {                                   // static LUTs only (no statistics in light programs)
 #pragma unroll
@@ -1112,7 +1417,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
                 for (int i = threadIdx.x; i < 768; i += blockDim.x)
                     s_lut[j][i] = (uint8_t)lut_entry_static(s_prog.op[j], (uint32_t)(i & 255), 0u);
         __syncthreads();
-        if (s_prog.cls == C_LUT) {
+        if (s_prog.cls == C_LUT || s_prog.cls == C_GEOM) {       // (GEOM: the one LUT slot rides in the float table)
             for (int i = threadIdx.x; i < 768; i += blockDim.x) {
                 uint32_t v = (uint32_t)(i & 255), base = (uint32_t)(i & ~255);
                 if (lut_mask & 1u) v = s_lut[0][base + v];
@@ -1137,11 +1442,49 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     const int oy0 = P.geo[1].oy[band], oy1 = P.geo[1].oy[band + 1];
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
-    switch (cls) {
-    case C_PLAIN: final_rows_plain_lut<OUT, TAB, false>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
-    case C_LUT:   final_rows_plain_lut<OUT, TAB, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
-    case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
-    default:      final_rows<OUT, TAB, C_GEOM, false>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+    bool done = false;
+    if constexpr (OUT != OUT_U8_HWC) {
+        // lean octet paths (faa_fast.cuh) for the common geometry; everything else takes the generic evaluators
+        if ((cls == C_GEOM || cls == C_POINT) && octet_geometry(P, t) && band_fully_staged(c, t, oy0, oy1)) {
+            const int k0 = s_prog.op[0].kind, k1 = s_prog.op[1].kind;
+            if (cls == C_GEOM) {
+                const bool g0 = k0 == K_AFFINE || k0 == K_SHIFT;          // geometric op first, partner after it
+                const int pk = g0 ? k1 : k0;
+                if (pk == K_NONE || kind_uses_lut(pk)) {
+                    const bool has_lut = pk != K_NONE;
+                    const OpRec gop = g0 ? s_prog.op[0] : s_prog.op[1];
+                    float pad[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)                           // fill colour: lut(0) if the LUT runs after the gather
+                        pad[ch] = (has_lut && g0) ? s_ftab[ch * 256] : normalise<TAB>(P, s_norm, ch, 0u);
+                    RowShift rs;
+                    if (rowshift_of(gop, rs)) {
+                        if (has_lut) final_rows_rowshift<OUT, true>(P, s_ftab, pad, c, rs, t.flip, out_img, oy0, oy1);
+                        else final_rows_rowshift<OUT, TAB>(P, s_norm, pad, c, rs, t.flip, out_img, oy0, oy1);
+                    } else {
+                        if (has_lut) final_rows_affine<OUT, true>(P, s_ftab, pad, c, gop, t.flip, out_img, oy0, oy1);
+                        else final_rows_affine<OUT, TAB>(P, s_norm, pad, c, gop, t.flip, out_img, oy0, oy1);
+                    }
+                    done = true;
+                }
+            } else if (k1 == K_NONE && k0 == K_COLOR) {
+                const float alpha = bits_to_float(s_prog.op[0].a[0]);
+                if (s_prog.op[0].a[1]) final_rows_color<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+                else final_rows_color<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+                done = true;
+            } else if (k1 == K_NONE && k0 == K_CUTOUT) {
+                final_rows_cutout<OUT, TAB>(P, s_norm, c, s_prog.box[0], t.flip, out_img, oy0, oy1);
+                done = true;
+            }
+        }
+    }
+    if (!done) {
+        switch (cls) {
+        case C_PLAIN: final_rows_plain_lut<OUT, TAB, false>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
+        case C_LUT:   final_rows_plain_lut<OUT, TAB, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
+        case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+        default:      final_rows<OUT, TAB, C_GEOM, false>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+        }
     }
     zero_box_rows<OUT>(P, s_prog, out_img, oy0, oy1);
 }
@@ -1202,12 +1545,15 @@ uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad) {
 template <int OUT, int NSRC, bool TAB>
 static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     const size_t dyn = (size_t)p.geo[0].band_cap * NSRC + (size_t)p.mat_cap;
-    static size_t configured = 0;                   // per instantiation
-    if (dyn > configured) {
+    static size_t configured[kMaxDevices] = {};     // per instantiation AND per device (the attribute is per device)
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (dyn > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(faa_augment_kernel<OUT, NSRC, TAB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
-        configured = dyn;
+        configured[dev] = dyn;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
@@ -1222,22 +1568,34 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;    // overlap with the resolve kernel
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = p.pdl ? 2 : 1;
+    cfg.numAttrs = (p.pdl || p.chain) ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
 
 template <int OUT, bool TAB>
 static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
     const size_t dyn = (size_t)p.geo[1].band_cap;
-    static size_t configured = 0;
-    if (dyn > configured) {
+    static size_t configured[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (dyn > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(faa_augment_light_kernel<OUT, TAB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return e;
-        configured = dyn;
+        configured[dev] = dyn;
     }
-    faa_augment_light_kernel<OUT, TAB><<<dim3((unsigned)p.geo[1].bands, (unsigned)p.B, 1), kThreads, dyn, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.geo[1].bands, (unsigned)p.B, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.chain ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, faa_augment_light_kernel<OUT, TAB>, p);
 }
 
 template <int OUT>
@@ -1274,8 +1632,16 @@ cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, bool 
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream) {
     if (p.n <= 0) return cudaSuccess;
     int threads = p.n >= 1024 ? 1024 : ((p.n + 31) / 32) * 32;
-    faa_resolve_kernel<<<1, threads, 0, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, faa_resolve_kernel, p);
 }
 
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,

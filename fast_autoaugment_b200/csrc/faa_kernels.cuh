@@ -24,6 +24,9 @@ struct ResolveParams {
     int32_t first, n;           // images [first, first+n) of the arrays above
     int32_t H, W, out_h, out_w, n_sub, n_op, op_base, apply_tail;
     int32_t allow;              // bit 0: the pixel kernel has a materialisation chunk, bit 1: a global scratch image
+    int32_t* ready;             // optional: set to `ticket` (release) once programs / order / n_heavy are written
+    int32_t ticket;
+    int32_t pdl;                // launch with programmatic stream serialization (chained steps)
 };
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 
@@ -52,11 +55,18 @@ struct AugParams {
     int32_t bands;              // CTAs (== cluster size) per image of the cluster kernel (== geo[0].bands)
     BandGeom geo[2];            // [0] cluster kernel, [1] light streaming kernel
     uint32_t rcp_out_qpr, rcp_w, rcp_wq;   // 2^32 / ceil(out_w/4), 2^32 / W, 2^32 / (W/4)  (rounded up) for fastdiv
+    uint32_t rcp_opr;           // 2^32 / (W/8) (octet fast paths; 0 when W % 8 != 0)
+    int32_t octets;             // 1: 8-pixel fast paths allowed (W % 8 == 0, out size == image size, float output 16-byte aligned)
     int32_t stage;              // 1: TMA-stage the raw row band into shared memory
     int32_t band_cap;           // bytes of dynamic shared memory per staged band
     int32_t crop_pad;           // max |crop_dy| (RandomCrop padding)
     int32_t mat_cap;            // bytes of the materialisation chunk (0: none), a whole number of rows >= 3
     int32_t pdl;                // launched with programmatic stream serialization
+    const int32_t* ready;       // chained steps: spin until *ready == ticket before reading programs / order / n_heavy
+    int32_t ticket;
+    int32_t chain;              // 1: steps are chained with programmatic dependent launches on ONE stream - no
+                                // griddepcontrol.wait (nothing of the previous kernel is consumed), trigger the
+                                // dependents once this CTA has copied its program
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };

@@ -12,12 +12,15 @@
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import PIL.Image
 import torch
+from torch.utils.data import Sampler, SubsetRandomSampler
 
 from . import _lib, archive
+from .conf import Config as C
 from .engine import (CIFAR_MEAN, CIFAR_STD, IMAGENET_MEAN, IMAGENET_STD, CompiledPolicy, TailSpec,
                      augment_batch, make_rng)
 
@@ -81,7 +84,7 @@ class CutoutDefault(object):
 
 
 def policy_by_conf_name(aug):
-    """conf['aug'] -> policy list, with the reference's error behaviour (data.py:86-109)."""
+    """conf['aug'] -> policy list, with the reference's error behaviour (data.py:85-109)."""
     if isinstance(aug, list):
         return aug
     if aug in archive.BY_CONF_NAME:
@@ -91,66 +94,189 @@ def policy_by_conf_name(aug):
     raise ValueError("not found augmentations. %s" % aug)
 
 
-class GpuAugmentedLoader:
-    """Iterable of ``(augmented CUDA batch, labels)`` over a device-resident uint8 dataset.
+class SubsetSampler(Sampler):
+    """Reference ``SubsetSampler`` (data.py:349-362): the given indices, in order."""
 
-    images: uint8 [N,H,W,3] (numpy or tensor; moved to ``device`` once), labels: int64 [N].
-    Mirrors ``DataLoader(..., shuffle=True, drop_last=True)`` of reference data.py:214-216 for
-    the train loader; ``rank``/``world_size`` shard indices like ``DistributedSampler``
-    (data.py:205-212).  ``set_epoch`` reseeds the shuffle (train.py:252).
-    """
-
-    def __init__(self, images, labels, batch, policies, tail: TailSpec, device="cuda", shuffle=True,
-                 drop_last=True, seed=0, rank=0, world_size=1, parity=False):
-        if not torch.cuda.is_available():
-            raise _lib.FaaRuntimeError("fast_autoaugment_b200 needs a CUDA device (no CPU fallback)")
-        self.device = torch.device(device)
-        self.images = torch.as_tensor(images).to(self.device).contiguous()
-        self.labels = torch.as_tensor(labels).to(self.device)
-        self.batch, self.tail, self.shuffle, self.drop_last = batch, tail, shuffle, drop_last
-        self.seed, self.epoch, self.rank, self.world_size, self.parity = seed, 0, rank, world_size, parity
-        self.aug = Augmentation(policies) if policies is not None else Augmentation([[("Invert", 0.0, 0.0)]])
-        n = self.images.shape[0]
-        self.per_rank = n // world_size if drop_last else math.ceil(n / world_size)
-
-    def set_epoch(self, epoch):
-        self.epoch = epoch
-
-    def __len__(self):
-        return self.per_rank // self.batch if self.drop_last else math.ceil(self.per_rank / self.batch)
+    def __init__(self, indices):
+        self.indices = indices
 
     def __iter__(self):
-        n = self.images.shape[0]
-        g = torch.Generator(device="cpu")
-        g.manual_seed(self.seed + self.epoch)
-        order = torch.randperm(n, generator=g) if self.shuffle else torch.arange(n)
-        order = order[self.rank::self.world_size][: self.per_rank].to(self.device)
+        return (i for i in self.indices)
+
+    def __len__(self):
+        return len(self.indices)
+
+
+class DeviceDataset:
+    """uint8 images [N,H,W,3] + int64 targets living on the device - the counterpart of the reference's
+    torchvision dataset objects (``total_trainset`` / ``testset``, data.py:114-196); ``targets`` stays a host
+    list like torchvision's so that the stratified splits see what the reference's see."""
+
+    def __init__(self, images, targets, device="cuda"):
+        self.images = torch.as_tensor(np.ascontiguousarray(images) if isinstance(images, np.ndarray) else images)
+        if self.images.dtype != torch.uint8 or self.images.dim() != 4 or self.images.shape[-1] != 3:
+            raise ValueError("images must be uint8 [N, H, W, 3]")
+        self.images = self.images.to(device).contiguous()
+        self.targets = [int(t) for t in targets]
+        self.labels = torch.as_tensor(self.targets, dtype=torch.int64, device=device)
+
+    def __len__(self):
+        return self.images.shape[0]
+
+    def subset(self, idx):
+        idx = [int(i) for i in idx]
+        t = torch.as_tensor(idx, dtype=torch.int64, device=self.images.device)
+        d = DeviceDataset.__new__(DeviceDataset)
+        d.images = self.images.index_select(0, t)
+        d.targets = [self.targets[i] for i in idx]
+        d.labels = self.labels.index_select(0, t)
+        return d
+
+
+class GpuAugmentedLoader:
+    """What ``get_dataloaders`` hands to ``train.py:47`` / ``search.py:101`` instead of a torch ``DataLoader``:
+    an iterable of ``(data, label)`` whose ``data`` is the augmented, normalised CUDA batch (``.cuda()`` at
+    train.py:49 becomes a no-op).  Batching follows ``DataLoader(dataset, batch_size, shuffle, sampler,
+    drop_last)`` (reference data.py:214-224): the index stream comes from the very sampler objects the
+    reference builds; the pixels of a batch are gathered on the device and go through ONE fused launch
+    (policy -> RandomCrop -> HFlip -> ToTensor -> Normalize -> CutoutDefault).
+
+    ``parity=True`` replays the reference's per-sample draws from the global ``random`` / ``numpy.random`` /
+    torch generators (a ``num_workers=0`` DataLoader); the default draws on the device with Philox.
+    """
+
+    def __init__(self, dataset: DeviceDataset, batch, policies, tail: TailSpec, sampler=None, shuffle=False,
+                 drop_last=False, seed=None, parity=False):
+        if not torch.cuda.is_available():
+            raise _lib.FaaRuntimeError("fast_autoaugment_b200 needs a CUDA device (no CPU fallback)")
+        self.dataset, self.batch_size, self.tail = dataset, int(batch), tail
+        self.sampler, self.shuffle, self.drop_last, self.parity = sampler, shuffle, drop_last, parity
+        self.aug = Augmentation(policies) if policies is not None else Augmentation([[("Invert", 0.0, 0.0)]])
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        self._drawn = 0                   # samples drawn so far: the Philox counter never repeats across epochs
+
+    def _n(self):
+        return len(self.sampler) if self.sampler is not None else len(self.dataset)
+
+    def __len__(self):
+        n = self._n()
+        return n // self.batch_size if self.drop_last else math.ceil(n / self.batch_size)
+
+    def _indices(self):
+        if self.sampler is not None:
+            return list(iter(self.sampler))
+        n = len(self.dataset)
+        return torch.randperm(n).tolist() if self.shuffle else list(range(n))
+
+    def __iter__(self):
+        idx_all = self._indices()
+        dev = self.dataset.images.device
         for k in range(len(self)):
-            idx = order[k * self.batch:(k + 1) * self.batch]
-            raw = self.images.index_select(0, idx)
-            data = self.aug.augment_batch(raw, self.tail, seed=self.seed * 1000003 + self.epoch,
-                                          first_index=(self.rank * len(self) + k) * self.batch, parity=self.parity)
-            yield data, self.labels.index_select(0, idx)
+            idx = idx_all[k * self.batch_size:(k + 1) * self.batch_size]
+            t = torch.as_tensor(idx, dtype=torch.int64).to(dev, non_blocking=True)
+            raw = self.dataset.images.index_select(0, t)
+            data = self.aug.augment_batch(raw, self.tail, seed=self.seed, first_index=self._drawn, parity=self.parity)
+            self._drawn += len(idx)
+            yield data, self.dataset.labels.index_select(0, t)
 
 
-def get_dataloaders(dataset, batch, images, labels, aug="fa_reduced_cifar10", cutout=16, out_dtype=torch.float16,
-                    test_images=None, test_labels=None, rank=0, world_size=1, seed=0):
-    """Device-resident counterpart of reference ``get_dataloaders`` (data.py:37-225) for datasets
-    already in memory as uint8 arrays (there are no dataset files on the build / GPU boxes).
-    Returns ``(train_sampler, trainloader, validloader, testloader)`` like the reference; the
-    train loader doubles as its own sampler (``set_epoch``)."""
-    if "cifar" in dataset or "svhn" in dataset:
+# ---------------------------------------------------------------------------------------------------
+def _load_arrays(dataset, dataroot):
+    """(train images, train targets, test images, test targets) as uint8 / int arrays.
+
+    ``dataroot`` is the reference's dataset directory (torchvision layout, read with ``download=False`` - the
+    build and GPU boxes have no network), or a directory holding ``<dataset>_train.npz`` / ``<dataset>_test.npz``
+    (arrays ``data`` [N,H,W,3] uint8 and ``targets``), or - for in-memory injection (tests, synthetic benchmarks) -
+    a mapping ``{"train": (images, targets), "test": (images, targets)}``."""
+    base = dataset.replace("reduced_", "")
+    if isinstance(dataroot, dict):
+        tr, te = dataroot["train"], dataroot.get("test", dataroot["train"])
+        return np.asarray(tr[0]), list(tr[1]), np.asarray(te[0]), list(te[1])
+    npz = [os.path.join(str(dataroot), "%s_%s.npz" % (base, s)) for s in ("train", "test")]
+    if all(os.path.exists(p) for p in npz):
+        a, b = np.load(npz[0]), np.load(npz[1])
+        return a["data"], list(a["targets"]), b["data"], list(b["targets"])
+    import torchvision
+    if base in ("cifar10", "cifar100"):
+        cls = torchvision.datasets.CIFAR10 if base == "cifar10" else torchvision.datasets.CIFAR100
+        tr, te = cls(root=dataroot, train=True, download=False), cls(root=dataroot, train=False, download=False)
+        return tr.data, list(tr.targets), te.data, list(te.targets)
+    if base == "svhn":
+        def hwc(d):
+            return np.ascontiguousarray(np.transpose(d.data, (0, 2, 3, 1)))
+        tr = torchvision.datasets.SVHN(root=dataroot, split="train", download=False)
+        te = torchvision.datasets.SVHN(root=dataroot, split="test", download=False)
+        if dataset == "svhn":                                   # data.py:132-135: train + extra
+            ex = torchvision.datasets.SVHN(root=dataroot, split="extra", download=False)
+            return (np.concatenate([hwc(tr), hwc(ex)]), list(tr.labels) + list(ex.labels), hwc(te), list(te.labels))
+        return hwc(tr), list(tr.labels), hwc(te), list(te.labels)
+    raise ValueError("invalid dataset name=%s" % dataset) if "imagenet" not in dataset else NotImplementedError(
+        "ImageNet needs JPEG decoding (reference imagenet.py:80), which is outside this package's hot path: "
+        "pass fixed-size uint8 arrays through a mapping / .npz dataroot instead")
+
+
+def get_dataloaders(dataset, batch, dataroot, split=0.15, split_idx=0, multinode=False, target_lb=-1):
+    """Drop-in for reference ``get_dataloaders`` (data.py:37-225): same signature, same conf keys
+    (``C.get()['aug']``, ``['cutout']``), same stratified splits and sampler objects, same return tuple
+    ``(train_sampler, trainloader, validloader, testloader)`` - but the three loaders are
+    ``GpuAugmentedLoader`` s over device-resident uint8 datasets, so the per-sample PIL chain of the reference's
+    DataLoader workers is replaced by one fused kernel launch per batch.
+
+    Extra conf keys (optional): ``faa_out_dtype`` ('float32' default - what the reference yields -, 'float16',
+    'bfloat16'), ``faa_parity`` (replay the reference's global RNG draws per sample; tests)."""
+    from sklearn.model_selection import StratifiedShuffleSplit
+    import torch.distributed as dist
+
+    conf = C.get()
+    out_dtype = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}[
+        str(conf.get("faa_out_dtype", "float32"))]
+    cutout = int(conf.get("cutout", 0) or 0)
+    if "cifar" in dataset or "svhn" in dataset:                 # data.py:38-48
         tail = TailSpec((32, 32), 4, True, CIFAR_MEAN, CIFAR_STD, cutout, out_dtype)
         test_tail = TailSpec(None, 0, False, CIFAR_MEAN, CIFAR_STD, 0, out_dtype)
-    elif "imagenet" in dataset:
+    elif "imagenet" in dataset:                                 # data.py:49-80 on already-sized images (SURVEY.md 3-D)
         tail = TailSpec(None, 0, True, IMAGENET_MEAN, IMAGENET_STD, cutout, out_dtype)
         test_tail = TailSpec(None, 0, False, IMAGENET_MEAN, IMAGENET_STD, 0, out_dtype)
     else:
         raise ValueError("dataset=%s" % dataset)
-    policies = policy_by_conf_name(aug)
-    train = GpuAugmentedLoader(images, labels, batch, policies, tail, seed=seed, rank=rank, world_size=world_size)
-    valid = GpuAugmentedLoader(images[:0], labels[:0], batch, policies, tail, shuffle=False, drop_last=False)
-    test = None
-    if test_images is not None:
-        test = GpuAugmentedLoader(test_images, test_labels, batch, None, test_tail, shuffle=False, drop_last=False)
-    return train, train, valid, test
+    policies = policy_by_conf_name(conf["aug"])                 # data.py:85-109 (ValueError on an unknown name)
+
+    tr_x, tr_y, te_x, te_y = _load_arrays(dataset, dataroot)
+    if dataset in ("cifar10", "cifar100", "svhn", "imagenet"):
+        total_trainset, testset = DeviceDataset(tr_x, tr_y), DeviceDataset(te_x, te_y)
+    elif dataset in ("reduced_cifar10", "reduced_svhn"):        # data.py:117-126, 136-146
+        test_size = 46000 if dataset == "reduced_cifar10" else 73257 - 1000
+        sss = StratifiedShuffleSplit(n_splits=1, test_size=test_size, random_state=0)
+        train_idx, _ = next(sss.split(list(range(len(tr_y))), tr_y))
+        total_trainset, testset = DeviceDataset(tr_x, tr_y).subset(train_idx), DeviceDataset(te_x, te_y)
+    else:
+        raise ValueError("invalid dataset name=%s" % dataset)
+
+    train_sampler = None
+    if split > 0.0:                                             # data.py:189-203
+        sss = StratifiedShuffleSplit(n_splits=5, test_size=split, random_state=0)
+        sss = sss.split(list(range(len(total_trainset))), total_trainset.targets)
+        for _ in range(split_idx + 1):
+            train_idx, valid_idx = next(sss)
+        if target_lb >= 0:
+            train_idx = [i for i in train_idx if total_trainset.targets[i] == target_lb]
+            valid_idx = [i for i in valid_idx if total_trainset.targets[i] == target_lb]
+        train_sampler = SubsetRandomSampler(train_idx)
+        valid_sampler = SubsetSampler(valid_idx)
+        if multinode:
+            train_sampler = torch.utils.data.distributed.DistributedSampler(
+                torch.utils.data.Subset(range(len(total_trainset)), train_idx),
+                num_replicas=dist.get_world_size(), rank=dist.get_rank())
+    else:
+        valid_sampler = SubsetSampler([])
+        if multinode:
+            train_sampler = torch.utils.data.distributed.DistributedSampler(
+                range(len(total_trainset)), num_replicas=dist.get_world_size(), rank=dist.get_rank())
+
+    parity = bool(conf.get("faa_parity", False))
+    trainloader = GpuAugmentedLoader(total_trainset, batch, policies, tail, sampler=train_sampler,
+                                     shuffle=train_sampler is None, drop_last=True, parity=parity)       # data.py:214-216
+    validloader = GpuAugmentedLoader(total_trainset, batch, policies, tail, sampler=valid_sampler,
+                                     shuffle=False, drop_last=False, parity=parity)                      # data.py:217-219
+    testloader = GpuAugmentedLoader(testset, batch, None, test_tail, shuffle=False, drop_last=False)     # data.py:221-224
+    return train_sampler, trainloader, validloader, testloader

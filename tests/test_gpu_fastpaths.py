@@ -1,0 +1,91 @@
+"""GPU parity of the lean octet paths (csrc/faa_fast.cuh, the 8-pixel streaming loops) against the oracle.
+
+These paths only run for the common launch geometry (W % 8 == 0, float output of the image's own size, no
+crop) and, for the gathers / Color / Cutout, only in the light streaming kernel - so every case here is run
+twice: forced through the two-kernel split (FAA_SPLIT_MIN=0) and forced through the cluster kernel alone
+(FAA_SPLIT_MIN huge).  Each image of a launch gets its own sub-policy, odd images are mirrored.
+fp32 output must be bit-exact (exact ToTensor+Normalize table of the oracle's uint8 result); fp16 / bf16 must
+equal that fp32 value rounded once.
+"""
+import os
+import random
+
+import numpy as np
+import PIL.Image
+import pytest
+import torch
+
+from helpers import ALL_OPS, exact_norm_table, seed_all, synth_batch
+
+from fast_autoaugment_b200.engine import IMAGENET_MEAN, IMAGENET_STD, CIFAR_MEAN, CIFAR_STD, CompiledPolicy, TailSpec, augment_batch
+from oracle import pil_path
+
+pytestmark = pytest.mark.gpu
+
+GEO = ["ShearX", "ShearY", "TranslateX", "TranslateY", "Rotate", "TranslateXAbs", "TranslateYAbs"]
+LUTS = ["Invert", "Solarize", "Posterize", "Brightness", "Posterize2"]
+
+
+def _policies():
+    rng = random.Random(11)
+    levels = (0.0, 0.07, 0.31, 0.5, 0.75, 0.93, 1.0)
+    pols = [[(name, 1.0, lv), (name, 0.0, lv)] for name in ALL_OPS for lv in levels]          # single ops
+    pols += [[(name, 0.0, lv), (name, 1.0, lv)] for name in ALL_OPS for lv in (0.2, 0.8)]     # ... in slot 1
+    for g in GEO:                                                                              # gather + LUT partner, both orders
+        for l in LUTS:
+            pols.append([(g, 1.0, rng.random()), (l, 1.0, rng.random())])
+            pols.append([(l, 1.0, rng.random()), (g, 1.0, rng.random())])
+    for a in ("Color", "Cutout", "CutoutAbs"):                                                 # partners the lean paths do NOT take
+        for g in ("ShearX", "Rotate", "TranslateY"):
+            pols.append([(a, 1.0, rng.random()), (g, 1.0, rng.random())])
+            pols.append([(g, 1.0, rng.random()), (a, 1.0, rng.random())])
+    pols += [[("Color", 1.0, rng.random()), (l, 1.0, rng.random())] for l in LUTS]
+    pols += [[("Cutout", 1.0, rng.random()), ("Color", 1.0, rng.random())], [("Color", 1.0, 0.3), ("Color", 1.0, 0.9)],
+             [("Invert", 1.0, 0.3), ("Solarize", 1.0, 0.4)], [("AutoContrast", 1.0, 0.3), ("ShearX", 1.0, 0.9)],
+             [("TranslateX", 1.0, 0.9), ("Equalize", 1.0, 0.9)], [("Sharpness", 1.0, 0.9), ("TranslateY", 1.0, 0.1)]]
+    return pols
+
+
+@pytest.mark.parametrize("split_min", ["0", "1000000000000"])
+@pytest.mark.parametrize("shape,norm", [((48, 64), "imagenet"), ((224, 224), "imagenet"), ((56, 104), "cifar"), ((380, 376), "imagenet")])
+def test_octet_paths_match_oracle(shape, norm, split_min, monkeypatch):
+    monkeypatch.setenv("FAA_SPLIT_MIN", split_min)
+    H, W = shape
+    policies = _policies()
+    n = len(policies)
+    pol = CompiledPolicy(policies)
+    batch = synth_batch(n, shape, seed=H * 3 + W)
+    mean, std = (IMAGENET_MEAN, IMAGENET_STD) if norm == "imagenet" else (CIFAR_MEAN, CIFAR_STD)
+    seed_all(4)
+    want_u8 = np.stack([np.asarray(pil_path.PolicyTransform([policies[i]])(PIL.Image.fromarray(a)))
+                        for i, a in enumerate(batch)])
+    seed_all(4)
+    ss, bb = [], []
+    for i in range(n):
+        s, b = CompiledPolicy([policies[i]]).sample_parity(1, H, W)
+        s["sub"] = i
+        s["flip"] = i & 1
+        ss.append(s)
+        bb.append(b)
+    samples, boxes = np.concatenate(ss), np.concatenate(bb)
+    for i in range(1, n, 2):
+        want_u8[i] = want_u8[i][:, ::-1]
+    tab = torch.from_numpy(exact_norm_table(mean, std))
+    xc = torch.from_numpy(np.ascontiguousarray(want_u8)).permute(0, 3, 1, 2).long()
+    want = torch.stack([tab[c][xc[:, c]] for c in range(3)], 1)
+    x = torch.from_numpy(batch).cuda()
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        tail = TailSpec(None, 0, True, mean, std, 0, dt)
+        got = augment_batch(pol, x, tail, samples, boxes).cpu()
+        bad = [(i, policies[i]) for i in range(n) if not torch.equal(got[i], want[i].to(dt))]
+        assert not bad, (shape, dt, split_min, len(bad), bad[:6])
+    # CutoutDefault post-pass on top of the octet paths
+    tail = TailSpec(None, 0, True, mean, std, 16, torch.float32)
+    for i in range(n):
+        samples[i]["zero_box"] = (max(0, i % H - 8), min(H, i % H + 8), max(0, (3 * i) % W - 8), min(W, (3 * i) % W + 8))
+    got = augment_batch(pol, x, tail, samples, boxes).cpu()
+    for i in range(n):
+        zb = samples[i]["zero_box"]
+        w = want[i].clone()
+        w[:, zb[0]:zb[1], zb[2]:zb[3]] = 0
+        assert torch.equal(got[i], w), (i, policies[i])

@@ -387,36 +387,101 @@ def test_odd_geometries(shape, n):
 
 
 def test_device_resident_loader_matches_oracle_chain():
-    """get_dataloaders counterpart (reference data.py:37-225, row N1): device-resident uint8 dataset,
-    batches come out augmented on the GPU; in parity mode they equal the reference chain applied to
-    the same samples in the same order"""
-    from fast_autoaugment_b200.data import GpuAugmentedLoader, get_dataloaders
-    n, b = 96, 32
+    """get_dataloaders drop-in (reference data.py:37-225, row N1): reference signature + conf keys, device-resident
+    uint8 dataset, batches come out augmented on the GPU; in parity mode they equal the reference chain applied
+    to the same samples in the same order"""
+    from sklearn.model_selection import StratifiedShuffleSplit
+    from fast_autoaugment_b200.conf import Config as C
+    from fast_autoaugment_b200.data import DeviceDataset, GpuAugmentedLoader, SubsetSampler, get_dataloaders
+    n, b = 200, 32
     images = synth_batch(n, (32, 32), seed=50)
     labels = np.arange(n) % 10
     policies = archive.fa_reduced_cifar10()
     tail = TailSpec.cifar(16, torch.float32)
-    loader = GpuAugmentedLoader(images, labels, b, policies, tail, shuffle=False, parity=True)
+    loader = GpuAugmentedLoader(DeviceDataset(images[:96], labels[:96]), b, policies, tail, shuffle=False, parity=True)
     assert len(loader) == 3
     seed_all(13)
     got = [(d.cpu(), l.cpu()) for d, l in loader]
     seed_all(13)
-    want = pil_path.run_chain_on_batch(pil_path.cifar_train_chain(policies, 16), images)
+    want = pil_path.run_chain_on_batch(pil_path.cifar_train_chain(policies, 16), images[:96])
     assert torch.equal(torch.cat([d for d, _ in got]), want)
-    assert torch.equal(torch.cat([l for _, l in got]), torch.from_numpy(labels))
-    # fused-Philox loaders: deterministic per (seed, epoch), reshuffled by set_epoch, CUDA fp16 NCHW out
-    sampler, train, valid, test = get_dataloaders("cifar10", b, images, labels, aug="fa_reduced_cifar10", cutout=16,
-                                                  test_images=images[:b], test_labels=labels[:b])
-    a = [d.clone() for d, _ in train]
-    bb = [d.clone() for d, _ in train]
-    assert all(torch.equal(x, y) for x, y in zip(a, bb))
-    assert a[0].is_cuda and a[0].dtype == torch.float16 and tuple(a[0].shape) == (b, 3, 32, 32)
-    sampler.set_epoch(1)
-    c = [d.clone() for d, _ in train]
-    assert not torch.equal(a[0], c[0])
+    assert torch.equal(torch.cat([l for _, l in got]), torch.from_numpy(labels[:96]))
+    # the reference signature: conf-driven policy / cutout, stratified split, samplers, four return values
+    C.get().clear()
+    C.get().update({"aug": "fa_reduced_cifar10", "cutout": 16, "faa_parity": True})
+    root = {"train": (images, labels), "test": (images[:b], labels[:b])}
+    sampler, train, valid, test = get_dataloaders("cifar10", b, root, split=0.15, split_idx=1)
+    sss = StratifiedShuffleSplit(n_splits=5, test_size=0.15, random_state=0).split(list(range(n)), list(labels))
+    for _ in range(2):
+        tr_idx, va_idx = next(sss)
+    assert isinstance(sampler, torch.utils.data.SubsetRandomSampler) and list(sampler.indices) == list(tr_idx)
+    assert isinstance(valid.sampler, SubsetSampler) and list(valid.sampler.indices) == list(va_idx)
+    assert len(train) == len(tr_idx) // b and len(valid) == -(-len(va_idx) // b)
+    # the validation loader shares transform_train (data.py:217-219): policy + crop + flip + cutout, in order
+    seed_all(3)
+    got_v = torch.cat([d.cpu() for d, _ in valid])
+    lab_v = torch.cat([l.cpu() for _, l in valid])
+    seed_all(3)
+    want_v = pil_path.run_chain_on_batch(pil_path.cifar_train_chain(policies, 16), images[va_idx])
+    assert torch.equal(got_v, want_v) and torch.equal(lab_v, torch.from_numpy(labels[va_idx]))
+    # test loader: ToTensor + Normalize only (transform_test, data.py:45-48)
     t0 = next(iter(test))[0]
     ref = torch.from_numpy(np.stack([pil_path.fixed_shape_chain(None, pil_path.CIFAR_MEAN, pil_path.CIFAR_STD, False, 0)(
         PIL.Image.fromarray(im)).numpy() for im in images[:b]]))
-    assert torch.equal(t0.cpu(), ref.half())
+    assert t0.is_cuda and t0.dtype == torch.float32 and torch.equal(t0.cpu(), ref)
+    # fused-Philox production mode, fp16: every epoch draws new decisions; split=0 -> empty validation loader
+    C.get().update({"faa_parity": False, "faa_out_dtype": "float16"})
+    sampler, train, valid, test = get_dataloaders("cifar10", b, root, split=0.0)
+    assert sampler is None and len(valid) == 0 and len(train) == n // b
+    a = [d.clone() for d, _ in train]
+    assert a[0].is_cuda and a[0].dtype == torch.float16 and tuple(a[0].shape) == (b, 3, 32, 32)
+    # target_lb filters both index lists (data.py:196-198)
+    _, tr1, va1, _ = get_dataloaders("cifar10", b, root, split=0.15, target_lb=3)
+    assert all(int(l) == 3 for _, ls in va1 for l in ls) and len(tr1.sampler) == sum(1 for i in StratifiedShuffleSplit(
+        n_splits=5, test_size=0.15, random_state=0).split(list(range(n)), list(labels)).__next__()[0] if labels[i] == 3)
     with pytest.raises(ValueError):
-        get_dataloaders("mnist", b, images, labels)
+        get_dataloaders("mnist", b, root)
+    C.get().update({"aug": "no_such_policy"})
+    with pytest.raises(ValueError):
+        get_dataloaders("cifar10", b, root)
+    C.get().clear()
+
+
+def test_reference_train_loop_body_runs_unchanged():
+    """reference train.py:47-58 (the body of run_epoch) against the drop-in loaders and mixup: `.cuda()` on the
+    yielded tensors is a no-op, mixup returns the reference's 4-tuple, a WRN-style step consumes the batch"""
+    from fast_autoaugment_b200.aug_mixup import mixup
+    from fast_autoaugment_b200.conf import Config as C
+    from fast_autoaugment_b200.data import get_dataloaders
+    n, b = 256, 64
+    images = synth_batch(n, (32, 32), seed=3)
+    labels = np.arange(n) % 10
+    C.get().clear()
+    C.get().update({"aug": "fa_reduced_cifar10", "cutout": 16, "mixup": 0.2, "epoch": 1})
+    _, loader, _, _ = get_dataloaders("cifar10", b, {"train": (images, labels)}, split=0.0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1),
+                                torch.nn.Flatten(), torch.nn.Linear(8, 10)).cuda()
+    optimizer = torch.optim.SGD(model.parameters(), lr=0.01)
+    ce = torch.nn.CrossEntropyLoss()
+    total_steps = len(loader)
+    steps = 0
+    for data, label in loader:                                    # train.py:47
+        steps += 1
+        ptr = data.data_ptr()
+        data, label = data.cuda(), label.cuda()                   # train.py:49
+        assert data.data_ptr() == ptr and data.dtype == torch.float32
+        if C.get().conf.get('mixup', 0.0) <= 0.0 or optimizer is None:
+            preds = model(data)
+            loss = ce(preds, label)
+        else:                                                     # train.py:54-58
+            data, targets, shuffled_targets, lam = mixup(data, label, C.get()['mixup'])
+            preds = model(data)
+            loss = lam * ce(preds, targets) + (1 - lam) * ce(preds, shuffled_targets)
+            assert 0.5 <= lam <= 1.0 and targets.shape == shuffled_targets.shape
+            del shuffled_targets, lam
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        assert torch.isfinite(loss)
+    assert steps == total_steps == n // b
+    C.get().clear()
