@@ -13,7 +13,7 @@ and calling it without a CUDA device raises - there is no CPU fallback.
 """
 from . import _lib                      # noqa: F401  (fails loudly if the CUDA library is missing)
 from . import archive                   # noqa: F401
-from .engine import (CompiledPolicy, FusedAugmenter, TailSpec, augment_batch, make_rng,   # noqa: F401
+from .engine import (CompiledPolicy, FusedAugmenter, TailSpec, augment_batch, augment_tta, make_rng,   # noqa: F401
                      CIFAR_MEAN, CIFAR_STD, IMAGENET_MEAN, IMAGENET_STD)
 from .data import Augmentation, CutoutDefault, GpuAugmentedLoader, get_dataloaders   # noqa: F401
 from .aug_mixup import mixup                                                      # noqa: F401

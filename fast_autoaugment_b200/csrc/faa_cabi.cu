@@ -219,6 +219,8 @@ struct faa_policy {
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaStream_t light_stream = nullptr; cudaEvent_t ev_res = nullptr, ev_light = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_host_done = nullptr; bool host_in_flight = false;   // faa_augment_host: last call's work (it owns d_in / stages)
+    std::mutex call_mu;                  // launches of one policy are serialised (speculation state, slots, staging)
     int device = -1;                     // the device that owns every buffer / stream / event above (-1: none yet)
     int32_t ticket = 0;                  // chained steps: id of the last resolve launch
     int32_t ahead_ticket = 0;
@@ -324,6 +326,7 @@ int faa_policy_destroy(faa_policy_t* p) {
         if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
     }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_host_done) cudaEventDestroy(p->ev_host_done);
     if (p->light_stream) cudaStreamDestroy(p->light_stream);
     if (p->ahead_stream) cudaStreamDestroy(p->ahead_stream);
     if (p->ev_ahead) cudaEventDestroy(p->ev_ahead);
@@ -427,6 +430,7 @@ int faa_sample_policy_mt(const faa_policy_t* pc, int batch, int h, int w, uint32
             faa_box_t& bx = out_boxes[(size_t)i * p->n_op + j];
             bx.x0 = bx.y0 = 0; bx.x1 = bx.y1 = -1;
             size_t k = (size_t)sub * p->n_op + j;
+            if (p->probs[k] < 0.0) continue;                                   // padding slot of a ragged sub-policy: no draw
             if (py.real53() > p->probs[k]) continue;                           // data.py:261
             const Compiled& c0 = tab[k * 2];
             if (c0.err) return fail(c0.err, std::string("applied op is invalid: ") +
@@ -526,6 +530,16 @@ static int normalisation(faa_policy* p, const faa_tail_t* tail, AugParams& P, bo
 
 static int out_elem_size(int dtype) { return dtype == FAA_F32 ? 4 : dtype == FAA_U8_HWC ? 1 : 2; }
 
+// RandomCrop offsets travel as int8 (faa_sample_t): ranges that do not fit are refused, never silently changed
+static int check_crop(int h, int w, const faa_tail_t* tail, int crop_pad) {
+    const int span_y = h + 2 * crop_pad - tail->out_h, span_x = w + 2 * crop_pad - tail->out_w;
+    if (span_y < 0 || span_x < 0)
+        return fail(FAA_ERR_VALUE, "Required crop size is larger than the (padded) input image size");   // torchvision's message
+    if (crop_pad > 127 || span_y - crop_pad > 127 || span_x - crop_pad > 127)
+        return fail(FAA_ERR_UNSUPPORTED, "RandomCrop offsets beyond +-127 pixels are not supported (int8 records): crop on the host side");
+    return FAA_OK;
+}
+
 static int check_tail(const faa_tail_t* tail) {
     if (!tail) return fail(FAA_ERR_VALUE, "null tail");
     if (tail->out_h <= 0 || tail->out_w <= 0 || tail->out_h > FAA_MAX_DIM || tail->out_w > FAA_MAX_DIM)
@@ -539,6 +553,7 @@ int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t
     if (!p || !rng || !d_samples || !d_boxes) return fail(FAA_ERR_VALUE, "null argument");
     if (int e = check_shape(h, w)) return e;
     if (int e = check_tail(tail)) return e;
+    if (int e = check_crop(h, w, tail, rng->crop_pad > 0 ? rng->crop_pad : 0)) return e;
     if (int e = ensure_device()) return e;
     if (int e = bind_device(p)) return e;
     const OpRec* d_ops = nullptr;
@@ -556,13 +571,14 @@ int faa_sample_philox(faa_policy_t* p, int batch, int h, int w, const faa_tail_t
 static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch,
                           int h, int w, const faa_tail_t* tail, const faa_sample_t* d_samples,
                           const faa_box_t* d_boxes, const faa_rng_t* rng, int op_base, const int32_t* d_partner,
-                          float lam, float oml, int apply_tail, bool allow_ahead, void* stream_v) {
+                          float lam, float oml, int apply_tail, bool allow_ahead, void* stream_v, int in_mod = 0) {
     if (!p || (!d_in_all && batch > 0) || (!d_out && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
     if (batch < 0 || first < 0 || first + batch > n_all) return fail(FAA_ERR_VALUE, "bad batch range");
     if (batch > 65535) return fail(FAA_ERR_UNSUPPORTED, "at most 65535 images per call (one grid row per image): split the batch");
     if (int e = check_shape(h, w)) return e;
     if (int e = check_tail(tail)) return e;
     if (!d_samples && !rng) return fail(FAA_ERR_VALUE, "need either resolved samples or an rng config");
+    if (rng && !d_samples && apply_tail) { if (int e = check_crop(h, w, tail, rng->crop_pad > 0 ? rng->crop_pad : 0)) return e; }
     if (op_base < 0 || op_base >= p->n_op) return fail(FAA_ERR_VALUE, "op_base out of range");
     if (tail->out_dtype == FAA_U8_HWC && d_partner) return fail(FAA_ERR_UNSUPPORTED, "mixup needs a float output");
     if (int e = ensure_device()) return e;
@@ -584,8 +600,8 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             }
             need = need < 65536 ? 65536 : need * 2;
             CK(cudaMalloc(&p->d_progs, 2 * need));                                                // two slots (resolve-ahead)
-            CK(cudaMalloc(&p->d_order, 2 * (3 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));  // order + per-launch counters + ready words, x2
-            CK(cudaMemset(p->d_order, 0, 2 * (3 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));
+            CK(cudaMalloc(&p->d_order, 2 * (4 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));  // order + 2 counters per launch + ready words, x2
+            CK(cudaMemset(p->d_order, 0, 2 * (4 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));
             p->d_progs_bytes = need;
             p->ahead_valid = false;
         }
@@ -594,7 +610,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     AugParams P; memset(&P, 0, sizeof P);
     P.in = d_in_all; P.out = d_out;
     P.partner = d_partner;
-    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.first = first;
+    P.B = batch; P.H = h; P.W = w; P.out_h = tail->out_h; P.out_w = tail->out_w; P.first = first; P.in_mod = in_mod;
     P.use_zero_box = (tail->use_zero_box && apply_tail) ? 1 : 0;
     P.lam = lam; P.one_minus_lam = oml;
     P.bands = pick_bands(h, w, tail->out_h, tail->out_w);
@@ -675,15 +691,21 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (const char* e = getenv("FAA_CHAIN")) chain_mode = atoi(e);
     const bool use_chain = chain_mode != 0 && use_split && allow_ahead && rng && !d_samples && !d_partner &&
                            !(getenv("FAA_AHEAD") && getenv("FAA_AHEAD")[0] == '0');
-    // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[cap] + ready[cap]
+    // Three-way split: statistics-LUT and Sharpness programs run in the lean mid kernel.
+    // Needs the geometry its paths assume: float planes of the image's own size, no crop, W % 4 == 0, staged bands.
+    static const bool mid_off = [] { const char* e = getenv("FAA_MID"); return e && e[0] == '0'; }();
+    const bool use_mid = use_split && !mid_off && P.stage && (w & 3) == 0 && tail->out_w == w && tail->out_h == h &&
+                         P.crop_pad == 0 && ((uintptr_t)d_out % 16) == 0;
+    if (use_mid) R.split = 2;
+    // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[2 cap] + ready[cap]
     const size_t cap_imgs = p->d_progs_bytes / sizeof(Prog);
     auto bind_slot = [&](int slot, ResolveParams& r, AugParams* a) {
         Prog* progs = reinterpret_cast<Prog*>((uint8_t*)p->d_progs + (size_t)slot * p->d_progs_bytes);
-        int32_t* order = reinterpret_cast<int32_t*>(p->d_order) + (size_t)slot * (3 * cap_imgs + 8);
-        // light programs run in their own streaming kernel; its counter lives behind the order array,
-        // indexed by `first` so that concurrent chunk launches do not share it (same for the ready word)
-        int32_t* counter = order + cap_imgs + first;
-        int32_t* ready = order + 2 * cap_imgs + first;
+        int32_t* order = reinterpret_cast<int32_t*>(p->d_order) + (size_t)slot * (4 * cap_imgs + 8);
+        // the segment counters of a split launch live behind the order array, indexed by `first` so that
+        // concurrent chunk launches do not share them (same for the ready word)
+        int32_t* counter = order + cap_imgs + 2 * (size_t)first;
+        int32_t* ready = order + 3 * cap_imgs + first;
         r.progs = progs; r.order = use_order ? order : nullptr; r.n_heavy = use_split ? counter : nullptr;
         r.ready = use_chain ? ready : nullptr;
         if (a) {
@@ -709,16 +731,26 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (spec_ok) {
         key.seed = rng->seed; key.first_index = rng->first_index;
         const int32_t v[16] = {batch, n_all, first, h, w, tail->out_h, tail->out_w, op_base, apply_tail, R.allow, R.split,
-                               rng->crop_pad, rng->hflip, rng->zero_box_len, use_order ? 1 : 0, use_chain ? 1 : 0};
+                               rng->crop_pad, rng->hflip, rng->zero_box_len, (use_order ? 1 : 0) | (in_mod << 1), use_chain ? 1 : 0};
         memcpy(key.v, v, sizeof v);
     }
+    auto set_mid_geometry = [&](AugParams& a) {
+        int mb = P.bands;                                   // halve the band count while a band (+ halo) stays <= 40 KB
+        while (mb > 1 && band_capacity(mb / 2, h, w, tail->out_h, 0) <= 40 * 1024) mb /= 2;
+        static const int mid_bands = [] { const char* e = getenv("FAA_MID_BANDS"); return e ? atoi(e) : 0; }();
+        if (mid_bands >= 1 && mid_bands <= 8 && (mid_bands & (mid_bands - 1)) == 0 && mid_bands <= h) mb = mid_bands;
+        a.bands = mb;
+        fill_geom(a.geo[0], mb, h, w, tail->out_h, 0, true);
+        a.band_cap = a.geo[0].band_cap; a.mat_cap = 0;
+    };
     const bool hit = spec_ok && p->ahead_valid && memcmp(&key, &p->ahead_key, sizeof key) == 0;
     int slot = p->cur_slot;
     if (use_chain) {
         // ---- chained schedule -------------------------------------------------------------------------
         // A step may only overlap the previous one if it neither reads what that step wrote nor writes what it
         // read or wrote (and follows it on the same stream); otherwise its first kernel is a plain dependent launch.
-        const uintptr_t in0 = (uintptr_t)d_in_all + (size_t)first * img_bytes, in1 = in0 + (size_t)batch * img_bytes;
+        const uintptr_t in0 = (uintptr_t)d_in_all + (in_mod ? 0 : (size_t)first * img_bytes),
+                        in1 = in0 + (size_t)(in_mod ? in_mod : batch) * img_bytes;
         const uintptr_t out0 = (uintptr_t)d_out, out1 = out0 + (size_t)batch * tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
         auto overlap = [](uintptr_t a0, uintptr_t a1, const uintptr_t b[2]) { return a0 < b[1] && b[0] < a1; };
         bool overlap_ok = p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
@@ -757,14 +789,14 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             p->ahead_key = key; p->ahead_key.first_index = rng->first_index + stride;
             p->ahead_slot = slot ^ 1; p->ahead_valid = true; p->ahead_ticket = R2.ticket;
         }
-        if (chain_mode == 2) {
-            CK(launch_augment(Pc, tail->out_dtype, use_tab, true, stream));
-            CK(launch_augment(Pc, tail->out_dtype, use_tab, false, stream));
-        } else {
-            CK(launch_augment(Pc, tail->out_dtype, use_tab, false, stream));
-            CK(launch_augment(Pc, tail->out_dtype, use_tab, true, stream));
+        AugParams Pm = Pc;                                  // the mid kernel: its own (taller) bands in bands / geo[0]
+        if (use_mid) set_mid_geometry(Pm);
+        const int order3[3] = {chain_mode == 2 ? 1 : 0, 2, chain_mode == 2 ? 0 : 1};   // default: cluster, mid, light
+        for (int k = 0; k < 3; ++k) {
+            const int which = order3[k];
+            if (which == 2) { if (use_mid) { CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, stream)); g_launches++; } }
+            else { CK(launch_augment(Pc, tail->out_dtype, use_tab, which, stream)); g_launches++; }
         }
-        g_launches += 2;
         p->chain_live = true; p->chain_stream = stream;
         p->prev_in[0] = in0; p->prev_in[1] = in1; p->prev_out[0] = out0; p->prev_out[1] = out1;
         return FAA_OK;
@@ -826,20 +858,22 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         static const bool prio_off = [] { const char* e = getenv("FAA_PRIO"); return e && e[0] == '0'; }();
         if (prio_off) {
             CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
-            CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
-            CK(launch_augment(P, tail->out_dtype, use_tab, true, p->light_stream));
+            CK(launch_augment(P, tail->out_dtype, use_tab, 0, stream));
+            CK(launch_augment(P, tail->out_dtype, use_tab, 1, p->light_stream));
+            if (use_mid) { AugParams Pm = P; Pm.pdl = 0; set_mid_geometry(Pm); CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, p->light_stream)); g_launches++; }
             CK(cudaEventRecord(p->ev_light, p->light_stream));
         } else {
             AugParams Ph = P; Ph.pdl = 0;                           // not behind the resolve kernel in its stream
             CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
-            CK(launch_augment(P, tail->out_dtype, use_tab, true, stream));
-            CK(launch_augment(Ph, tail->out_dtype, use_tab, false, p->light_stream));
+            CK(launch_augment(P, tail->out_dtype, use_tab, 1, stream));
+            CK(launch_augment(Ph, tail->out_dtype, use_tab, 0, p->light_stream));
+            if (use_mid) { AugParams Pm = Ph; set_mid_geometry(Pm); CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, p->light_stream)); g_launches++; }
             CK(cudaEventRecord(p->ev_light, p->light_stream));
         }
         CK(cudaStreamWaitEvent(stream, p->ev_light, 0));
         g_launches += 2;
     } else {
-        CK(launch_augment(P, tail->out_dtype, use_tab, false, stream));
+        CK(launch_augment(P, tail->out_dtype, use_tab, 0, stream));
         g_launches++;
     }
     return FAA_OK;
@@ -850,11 +884,25 @@ int faa_augment(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, in
                 void* stream) {
     if (!p) return fail(FAA_ERR_VALUE, "null policy");
     // intermediate launch of a chained policy = not the last 2-op window
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
     int apply_tail = (op_base + FAA_MAX_FUSED_OPS >= p->n_op) ? 1 : 0;
     if (!apply_tail && tail && (tail->out_dtype != FAA_U8_HWC || tail->out_h != h || tail->out_w != w))
         return fail(FAA_ERR_VALUE, "intermediate launches of a chained policy must write uint8 HWC at the input size");
     return augment_common(p, d_in, batch, 0, d_out, batch, h, w, tail, d_samples, d_boxes, rng, op_base, nullptr,
                           1.0f, 0.0f, apply_tail, p->n_op <= FAA_MAX_FUSED_OPS, stream);
+}
+
+int faa_augment_tta(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, int replicas, int h, int w,
+                    const faa_tail_t* tail, const faa_rng_t* rng, void* stream) {
+    if (!p || !rng) return fail(FAA_ERR_VALUE, "null argument");
+    if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "replicated launches support policies of at most 2 ops");
+    if (batch < 0 || replicas < 1) return fail(FAA_ERR_VALUE, "bad batch / replicas");
+    if ((long long)batch * replicas > 65535) return fail(FAA_ERR_UNSUPPORTED, "batch * replicas must be <= 65535");
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    // one launch over batch * replicas schedule entries; entry v = r * batch + i reads image i and draws the decisions of
+    // global sample first_index + v: replica r equals a plain launch with first_index + r * batch
+    return augment_common(p, d_in, batch * replicas, 0, d_out, batch * replicas, h, w, tail, nullptr, nullptr, rng, 0, nullptr,
+                          1.0f, 0.0f, 1, true, stream, replicas > 1 ? batch : 0);
 }
 
 int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int first, void* d_out, int batch, int h,
@@ -863,6 +911,7 @@ int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int f
     if (!p) return fail(FAA_ERR_VALUE, "null policy");
     if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "fused mixup supports policies of at most 2 ops");
     if (!(lam >= 0.0f && lam <= 1.0f)) return fail(FAA_ERR_MAGNITUDE, "lam must be in [0, 1]");   // aug_mixup.py:20
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
     return augment_common(p, d_in_all, n_all, first, d_out, batch, h, w, tail, d_samples_all, d_boxes_all, rng, 0,
                           d_partner, lam, one_minus_lam, 1, false, stream);
 }
@@ -909,6 +958,11 @@ int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_
     if (batch <= 0) return FAA_OK;
     if (int e = bind_device(p)) return e;
     cudaStream_t stream = (cudaStream_t)stream_v;
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    // The policy owns the device input buffer and the pinned stages: the previous call's asynchronous copies must
+    // have finished before any of them is rewritten (a pageable source is memcpy'd into the stage right below)
+    if (p->host_in_flight) { CK(cudaEventSynchronize(p->ev_host_done)); p->host_in_flight = false; }
+    if (!p->ev_host_done) CK(cudaEventCreateWithFlags(&p->ev_host_done, cudaEventDisableTiming));
     const size_t in_img = (size_t)h * w * 3;
     const size_t out_img = (size_t)tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
     if (int e = grow_dev(&p->d_in, &p->d_in_bytes, in_img * batch)) return e;
@@ -962,6 +1016,8 @@ int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_
         CK(cudaEventRecord(p->ev_join[i], p->side[i]));
         CK(cudaStreamWaitEvent(stream, p->ev_join[i], 0));
     }
+    CK(cudaEventRecord(p->ev_host_done, stream));
+    p->host_in_flight = true;
     if (h_out && !out_pinned) {
         CK(cudaStreamSynchronize(stream));
         memcpy(h_out, p->h_out_stage, out_img * batch);

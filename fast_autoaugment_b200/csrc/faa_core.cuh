@@ -362,9 +362,12 @@ FAA_HD void philox_sample(const RngCfg& r, uint64_t index, const OpRec* ops, con
     U4 b0 = philox4x32_10(c, k0, k1);
     s.sub = (uint16_t)umulhi32(b0.x, (uint32_t)n_sub);
     s.flip = (uint8_t)(r.hflip ? (b0.y >> 31) : 0u);                     // torch.rand(1) < 0.5
-    int span = 2 * r.crop_pad + 1;
-    s.crop_dy = (int8_t)(r.crop_pad ? (int)umulhi32(b0.z, (uint32_t)span) - r.crop_pad : 0);
-    s.crop_dx = (int8_t)(r.crop_pad ? (int)umulhi32(b0.w, (uint32_t)span) - r.crop_pad : 0);
+    // torchvision RandomCrop.get_params: top in [0, H + 2p - out_h], left in [0, W + 2p - out_w] (data.py:40);
+    // offsets are stored relative to the unpadded image.  (The host rejects ranges that do not fit int8.)
+    const bool do_crop = r.crop_pad > 0 || out_h != H || out_w != W;
+    const int span_y = H + 2 * r.crop_pad - out_h + 1, span_x = W + 2 * r.crop_pad - out_w + 1;
+    s.crop_dy = (int8_t)(do_crop && span_y > 1 ? (int)umulhi32(b0.z, (uint32_t)span_y) - r.crop_pad : (do_crop ? -r.crop_pad : 0));
+    s.crop_dx = (int8_t)(do_crop && span_x > 1 ? (int)umulhi32(b0.w, (uint32_t)span_x) - r.crop_pad : (do_crop ? -r.crop_pad : 0));
     s.reserved = 0;
     s.zero_box[0] = s.zero_box[1] = s.zero_box[2] = s.zero_box[3] = 0;
     if (r.zero_box_len > 0) {                                             // data.py:239-246
@@ -541,6 +544,15 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
 // streaming kernel (no cluster, few registers); everything else runs in the cluster kernel.
 FAA_HD bool prog_is_light(const Prog& g) {
     return g.stat_mask == 0 && (g.cls == C_PLAIN || g.cls == C_LUT || g.cls == C_POINT || g.cls == C_GEOM);
+}
+
+// "Mid" programs: whole-image statistics feeding per-channel LUTs, or Sharpness (+ a static LUT) - they need a
+// cluster (statistics exchange) or only halo rows, but none of the cluster kernel's materialisation / generic
+// machinery: they run in their own lean kernel when the launch geometry allows it (three-way split).
+FAA_HD bool prog_is_mid(const Prog& g) {
+    const int k1 = g.op[1].kind;
+    if (g.cls == C_LUT) return g.stat_mask != 0;
+    return g.cls == C_SHARP && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
 }
 
 // Rough relative cost of an image (per-pixel work units) - only used to schedule the

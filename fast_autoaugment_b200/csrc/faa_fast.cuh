@@ -97,34 +97,45 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
         T* o = dst + 8u * i;
         if ((unsigned)ys >= (unsigned)H || sx0 + 7 + (s7 - s0) < 0 || sx0 >= W) {
             fill_oct<OUT>(o, plane, pad);                                 // nothing of the octet has a source
-        } else if (s0 == s7 && sx0 >= 0 && sx0 + 7 < W) {
-            // all eight sources exist: 24 contiguous bytes from byte B0 of the image
-            const uint32_t B0 = (uint32_t)ys * pitch + (uint32_t)sx0 * 3u, k = B0 & 3u, A = B0 - k;
-            const uint32_t rel = A - c.s_lo;
+        } else if (s0 == s7) {
+            // One shift for the whole octet: its sources are 24 contiguous bytes from byte B0 of the image.  At a
+            // row edge only pixels [lo, hi) of the octet have a source; the aligned words are then clamped into the
+            // source row (valid memory, ignored bytes) and the missing pixels take the fill value.
+            const int lo = max(0, -sx0), hi = min(8, W - sx0);
+            const uint32_t vmask = (0xFFu >> (8 - hi)) & (0xFFu << lo) & 0xFFu;
+            const int row_lo = ys * (int)pitch, row_hi = row_lo + (int)pitch - 4;
+            const int B0 = row_lo + sx0 * 3, A = B0 & ~3;
+            const uint32_t k = (uint32_t)B0 & 3u;
+            const bool staged = (uint32_t)row_lo - c.s_lo <= s_len - pitch && s_len >= pitch;      // the whole source row
             uint32_t v[7];
-            if (rel <= s_len - 28u && s_len >= 28u) {                     // aligned words [A, A+28) are staged
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(c.sraw + rel);
+            if (staged) {
 #pragma unroll
-                for (int j = 0; j < 6; ++j) v[j] = p[j];
-                v[6] = k ? p[6] : 0u;
+                for (int j = 0; j < 7; ++j)
+                    v[j] = *reinterpret_cast<const uint32_t*>(c.sraw + ((uint32_t)min(max(A + 4 * j, row_lo), row_hi) - c.s_lo));
             } else {
-                const uint32_t* p = reinterpret_cast<const uint32_t*>(c.raw + A);
 #pragma unroll
-                for (int j = 0; j < 6; ++j) v[j] = __ldg(p + j);
-                v[6] = k ? __ldg(p + 6) : 0u;                             // never past the image: only read when it holds a source byte
+                for (int j = 0; j < 7; ++j) v[j] = __ldg(reinterpret_cast<const uint32_t*>(c.raw + min(max(A + 4 * j, row_lo), row_hi)));
             }
             uint32_t w[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) w[j] = __funnelshift_r(v[j], v[j + 1], 8u * k);
-            if (flip) stream_oct<OUT, USE_TAB, true>(P, w, tab, o, plane);
-            else stream_oct<OUT, USE_TAB, false>(P, w, tab, o, plane);
+            if (vmask == 0xFFu) {
+                if (flip) stream_oct<OUT, USE_TAB, true>(P, w, tab, o, plane);
+                else stream_oct<OUT, USE_TAB, false>(P, w, tab, o, plane);
+            } else {
+                uint32_t q[8], px[8];
+                unpack12(w[0], w[1], w[2], q); unpack12(w[3], w[4], w[5], q + 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) px[j] = flip ? q[7 - j] : q[j];
+                emit_oct_masked<OUT, USE_TAB>(P, tab, o, plane, px, flip ? (__brev(vmask) >> 24) : vmask, pad);
+            }
         } else {
-            // row edge or a shift break inside the octet: per pixel
+            // a shift break (Pillow's accumulated float offset) inside the octet: per pixel
             uint32_t px[8]; uint32_t valid = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int x = flip ? ax0 + 7 - j : ax0 + j;              // output pixel j of the octet
-                const int xs = x + (rs.shear ? s0 : rs.dx + (x >= rs.bx));
+                const int xs = x + rs.dx + (x >= rs.bx);
                 const bool ok = (unsigned)xs < (unsigned)W;
                 px[j] = ok ? load_raw(c, xs, ys) : 0u;
                 valid |= (uint32_t)ok << j;
@@ -137,57 +148,71 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------
-// General affine gather (ShearY, Rotate): one quad per thread and iteration, sources from global memory.
+// General affine gather (ShearY, Rotate).  Sources come from global memory (L1): a rotated band has no compact
+// source footprint.  To keep the gather coalesced each warp works on a tile of 128 consecutive output pixels in two
+// phases: (1) lane l fetches pixels l, l+32, l+64, l+96 of the tile - neighbouring lanes read neighbouring source
+// pixels, two aligned word loads and a funnel shift each - into a shared-memory tile; (2) lane l normalises pixels
+// 4l..4l+3 and writes 8-byte plane quads.  `tile`: 128 words per warp.
 template <int OUT, bool USE_TAB>
 __device__ __forceinline__ void final_rows_affine(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
-                                                  const OpRec op, int flip, void* out_img, int oy0, int oy1) {
+                                                  const OpRec op, int flip, void* out_img, int oy0, int oy1, uint32_t* tile) {
     using T = typename OutElem<OUT>::T;
     const int W = P.W, H = P.H;
-    const uint32_t qpr = (uint32_t)W >> 2;
-    const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
+    const uint32_t npx = (uint32_t)(oy1 - oy0) * (uint32_t)W;
     const uint32_t plane = (uint32_t)H * (uint32_t)W;
     T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
-    FastDiv dq; dq.init(qpr, P.rcp_wq);
-    uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
-    const uint32_t dr = dq.div(blockDim.x), dxq = blockDim.x - dr * qpr;
     const int a0 = op.a[0], a1 = op.a[1], a2 = op.a[2], a3 = op.a[3], a4 = op.a[4], a5 = op.a[5];
-    const int dfx = flip ? -a0 : a0, dfy = flip ? -a3 : a3;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t* my = tile + warp * 128u;
     const uint8_t* raw = c.raw;
-    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
-        const int y = oy0 + (int)r;
-        const int ax0 = flip ? W - 1 - (int)qx * 4 : (int)qx * 4;
-        int fx = a2 + a0 * ax0 + a1 * y, fy = a5 + a3 * ax0 + a4 * y;
-        uint32_t b[4][3]; uint32_t valid = 0;
+    FastDiv dw; dw.init((uint32_t)W, P.rcp_w);
+    for (uint32_t base = warp * 128u; base < npx; base += nwarp * 128u) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                                    // twelve byte loads, no branch in between
-            const int xs = fx >> 16, ys = fy >> 16;
-            const bool ok = (unsigned)xs < (unsigned)W && (unsigned)ys < (unsigned)H;
-            const uint8_t* p = raw + (ok ? (uint32_t)(ys * W + xs) * 3u : 0u);
-            b[k][0] = __ldg(p); b[k][1] = __ldg(p + 1); b[k][2] = __ldg(p + 2);
-            valid |= (uint32_t)ok << k;
-            fx += dfx; fy += dfy;
-        }
-        T* o = dst + 4u * q;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float v[4];
-            if (USE_TAB) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = tab[ch * 256 + b[k][ch]];
-            } else {
-                const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
-                const float2 r0 = __ffma2_rn(make_float2((float)b[0][ch], (float)b[1][ch]), sc, bi);
-                const float2 r1 = __ffma2_rn(make_float2((float)b[2][ch], (float)b[3][ch]), sc, bi);
-                v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t p = base + lane + 32u * (uint32_t)i;
+            uint32_t v = 0u;
+            if (p < npx) {
+                const uint32_t r = dw.div(p);
+                const int x = (int)(p - r * (uint32_t)W), y = oy0 + (int)r;
+                const int ax = flip ? W - 1 - x : x;
+                const int xs = (a2 + a0 * ax + a1 * y) >> 16, ys = (a5 + a3 * ax + a4 * y) >> 16;
+                const bool ok = (unsigned)xs < (unsigned)W && (unsigned)ys < (unsigned)H;
+                const uint32_t off = ok ? (uint32_t)(ys * W + xs) * 3u : 0u;
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + (off & ~3u));
+                const uint32_t lo = __ldg(wp);
+                const uint32_t hi = (off & 2u) ? __ldg(wp + 1) : 0u;     // bytes 2,3 of the word: the pixel spills into the next one
+                const uint32_t px = __funnelshift_r(lo, hi, 8u * (off & 3u)) & 0xFFFFFFu;
+                v = ok ? (px | 0x01000000u) : 0u;                        // bit 24: the pixel has a source
             }
-            if (valid != 15u) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = ((valid >> k) & 1u) ? v[k] : pad[ch];
-            }
-            store_plane4<OUT>(o + ch * plane, v, true, 4);
+            my[lane + 32u * (uint32_t)i] = v;
         }
-        qx += dxq; r += dr;
-        if (qx >= qpr) { qx -= qpr; ++r; }
+        __syncwarp();
+        const uint32_t p0 = base + 4u * lane;
+        if (p0 < npx) {
+            const uint4 q4 = reinterpret_cast<const uint4*>(my)[lane];
+            const uint32_t px[4] = {q4.x, q4.y, q4.z, q4.w};
+            const uint32_t valid = (q4.x >> 24) | ((q4.y >> 24) << 1) | ((q4.z >> 24) << 2) | ((q4.w >> 24) << 3);
+            T* o = dst + p0;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float v[4];
+                if (USE_TAB) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = tab[ch * 256 + ((px[k] >> (8 * ch)) & 255u)];
+                } else {
+                    const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
+                    const float2 r0 = __ffma2_rn(make_float2((float)((px[0] >> (8 * ch)) & 255u), (float)((px[1] >> (8 * ch)) & 255u)), sc, bi);
+                    const float2 r1 = __ffma2_rn(make_float2((float)((px[2] >> (8 * ch)) & 255u), (float)((px[3] >> (8 * ch)) & 255u)), sc, bi);
+                    v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
+                }
+                if (valid != 15u) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = ((valid >> k) & 1u) ? v[k] : pad[ch];
+                }
+                store_plane4<OUT>(o + ch * plane, v, true, 4);
+            }
+        }
+        __syncwarp();
     }
 }
 

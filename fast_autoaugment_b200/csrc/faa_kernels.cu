@@ -32,6 +32,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 
 #include "faa_kernels.cuh"
@@ -79,10 +80,10 @@ __device__ __forceinline__ int cost_bucket(uint32_t cost) {     // 0 = most expe
 }
 
 __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant__ ResolveParams P) {
-    __shared__ int s_count[2 * kCostBuckets], s_base[2 * kCostBuckets];
+    __shared__ int s_count[3 * kCostBuckets], s_base[3 * kCostBuckets];
     // let the dependent pixel kernel start launching (its prologue overlaps this kernel)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x < 2 * kCostBuckets) s_count[threadIdx.x] = 0;
+    if (threadIdx.x < 3 * kCostBuckets) s_count[threadIdx.x] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {
         const int i = P.first + t;
@@ -101,7 +102,9 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
         if (P.progs != nullptr) {
             Prog g;
             build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, P.allow, g);
-            g.bucket = (uint8_t)(cost_bucket(prog_cost(g)) + ((P.split && prog_is_light(g)) ? kCostBuckets : 0));
+            // weight class: 0 heavy (cluster kernel), 1 mid (statistics / Sharpness kernel, three-way split only), 2 light
+            const int wc = !P.split ? 0 : prog_is_light(g) ? 2 : (P.split == 2 && prog_is_mid(g)) ? 1 : 0;
+            g.bucket = (uint8_t)(cost_bucket(prog_cost(g)) + wc * kCostBuckets);
             P.progs[i] = g;
             atomicAdd(&s_count[g.bucket], 1);
         }
@@ -119,8 +122,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int b = 0; b < 2 * kCostBuckets; ++b) {
-            if (b == kCostBuckets && P.n_heavy != nullptr) *P.n_heavy = acc;      // images [0, acc) of the order are heavy
+        for (int b = 0; b < 3 * kCostBuckets; ++b) {
+            // schedule segments: [0, n_heavy[0]) heavy, [n_heavy[0], n_heavy[1]) mid, [n_heavy[1], n) light
+            if (b == kCostBuckets && P.n_heavy != nullptr) P.n_heavy[0] = acc;
+            if (b == 2 * kCostBuckets && P.n_heavy != nullptr) P.n_heavy[1] = acc;
             s_base[b] = acc; acc += s_count[b]; s_count[b] = 0;
         }
     }
@@ -157,6 +162,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(b), "r"(phase) : "memory");
     }
+}
+
+// TTA replicas (search.py:87-125): schedule entry v of a replicated launch augments input image v % in_mod with
+// its own decisions; in_mod == 0: one input image per entry
+__device__ __forceinline__ uint32_t src_image(const AugParams& P, int idx) {
+    return P.in_mod ? (uint32_t)idx % (uint32_t)P.in_mod : (uint32_t)idx;
 }
 
 // chained steps: programs / order / n_heavy of this step are complete once *ready == ticket (written with
@@ -886,12 +897,12 @@ __device__ __forceinline__ void final_rows_stream8(const AugParams& P, const flo
 
 // PLAIN / LUT final pass: the streaming loop when possible, else the generic aligned loop.
 // `ftab` (768 floats) is only read for LUT programs and must hold normalise(ch, lutc[ch][b]).
-template <int OUT, bool TAB, bool LUT>
+template <int OUT, bool TAB, bool LUT, bool OCT = false>
 __device__ __forceinline__ void final_rows_plain_lut(const AugParams& P, const float* s_norm, const float* ftab, const Ctx& c,
                                                      const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1) {
     if constexpr (OUT != OUT_U8_HWC) {
         if ((!LUT || ftab != nullptr) && band_fully_staged(c, t, oy0, oy1)) {
-            if (octet_geometry(P, t)) {
+            if (OCT && octet_geometry(P, t)) {                 // (the light kernel: 8 pixels per thread and iteration)
                 if (t.flip) {
                     if (LUT) final_rows_stream8<OUT, true, true>(P, ftab, c, out_img, oy0, oy1);
                     else final_rows_stream8<OUT, TAB, true>(P, s_norm, c, out_img, oy0, oy1);
@@ -1281,7 +1292,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     if (threadIdx.x == 0 && s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s)
-            tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_idx[s] * img_bytes + s_lo, s_len);
+            tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_image(P, src_idx[s]) * img_bytes + s_lo, s_len);
     }
     // per-image programs -> shared memory (24 words each)
 #pragma unroll
@@ -1303,7 +1314,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
-    const uint8_t* raw0 = P.in + (size_t)src_idx[0] * img_bytes;
+    const uint8_t* raw0 = P.in + (size_t)src_image(P, src_idx[0]) * img_bytes;
     bool any_stats = false;
 
     if constexpr (NSRC == 1) {
@@ -1324,49 +1335,18 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
             cg2.op[0] = c.op[1]; cg2.box[0] = c.box[1]; cg2.op[1].kind = K_NONE;
             final_rows_cls<OUT, TAB>(C_SG, P, s_norm, cg2, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1);
         } else {
+            any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
+            // LUT programs: composed LUT o normalisation table in the (now idle) slot-0 histogram
             float* ftab = nullptr;
-            bool peers_pending = false;
-            const TailInfo t0 = make_tail(P, st[0].prog);
-            if (OUT != OUT_U8_HWC && (P.W & 3) == 0 && scalar_stats_program(st[0].prog) && P.stage &&
-                band_fully_staged(c, TailInfo{0, 0, 0, 0, 0, 0, 0}, y0, y1)) {
-                // AutoContrast / Contrast [+ static LUT]: min / max or luma sum, one cluster barrier, direct table
+            if (OUT != OUT_U8_HWC && cls == C_LUT) {
                 ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
-                build_scalar_stats_table<TAB>(P, s_norm, st[0], c, y0, y1, cluster, ftab);
-                peers_pending = P.bands > 1;
-            } else {
-                any_stats = prepare_image(P, c, y0, y1, st[0], cluster);
-                // LUT programs: composed LUT o normalisation table in the (now idle) slot-0 histogram
-                if (OUT != OUT_U8_HWC && cls == C_LUT) {
-                    ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
-                    build_ftab<TAB>(P, s_norm, st[0].lutc, ftab);
-                }
+                build_ftab<TAB>(P, s_norm, st[0].lutc, ftab);
             }
-            bool done = false;
-            if constexpr (OUT != OUT_U8_HWC) {
-                const int k1 = st[0].prog.op[1].kind;
-                if (cls == C_SHARP && octet_geometry(P, t0) && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS) &&
-                    band_fully_staged(c, t0, max(oy0 - 1, 0), min(oy1 + 1, P.H))) {
-                    // Sharpness [+ static LUT]: byte-stream 3x3 (faa_fast.cuh); the partner LUT rides in the float table
-                    const float alpha = bits_to_float(st[0].prog.op[0].a[0]);
-                    const bool clip = st[0].prog.op[0].a[1] != 0;
-                    if (k1 != K_NONE) {
-                        ftab = reinterpret_cast<float*>(&st[0].hist[0][0]);
-                        build_ftab<TAB>(P, s_norm, st[0].lut[1], ftab);     // (prepare_image built the static LUT of slot 1)
-                        if (clip) final_rows_sharp4<OUT, true, true>(P, ftab, c, alpha, t0.flip, out_img, oy0, oy1);
-                        else final_rows_sharp4<OUT, true, false>(P, ftab, c, alpha, t0.flip, out_img, oy0, oy1);
-                    } else {
-                        if (clip) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t0.flip, out_img, oy0, oy1);
-                        else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t0.flip, out_img, oy0, oy1);
-                    }
-                    done = true;
-                }
-            }
-            if (!done) final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, t0, out_img, oy0, oy1, ftab);
-            if (peers_pending) cluster_wait();                             // peers have read this CTA's statistics record
+            final_rows_cls<OUT, TAB>(cls, P, s_norm, c, st[0].lutc, make_tail(P, st[0].prog), out_img, oy0, oy1, ftab);
         }
         zero_box_rows<OUT>(P, st[0].prog, out_img, oy0, oy1);
     } else {
-        const uint8_t* raw1 = P.in + (size_t)src_idx[1] * img_bytes;
+        const uint8_t* raw1 = P.in + (size_t)src_image(P, src_idx[1]) * img_bytes;
         const Ctx c0 = make_ctx(P, raw0, s_dyn, s_lo, s_len, P.H, P.W, st[0], true);
         const Ctx c1 = make_ctx(P, raw1, s_dyn + P.band_cap, s_lo, s_len, P.H, P.W, st[1], true);
         any_stats = prepare_image(P, c0, y0, y1, st[0], cluster);
@@ -1375,6 +1355,75 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     }
 
     (void)any_stats;   // statistics exchanges end with their own cluster barrier (build_slot_lut)
+}
+
+// ---------------------------------------------------------------------------------------
+// launch 2b: the "mid" kernel of a three-way split: statistics -> per-channel LUT programs (AutoContrast, Equalize,
+// Contrast, with static LUT partners) and Sharpness (+ static LUT).  One cluster per image like the cluster kernel
+// (P.bands / P.geo[0] of THIS launch: fewer, taller bands - the per-CTA overhead of a statistics program is
+// amortised over more pixels), but only the lean paths: scalar statistics with one cluster barrier, the shared
+// histogram path for Equalize and pushed-forward histograms, the byte-stream Sharpness, the streaming final pass.
+// Preconditions (host, three-way split only): float output of the image's own size, no crop, W % 4 == 0, staged bands.
+// It owns schedule entries [n_heavy[0], n_heavy[1]).
+template <int OUT, bool TAB>
+__global__ void __launch_bounds__(kThreads, 4) faa_augment_mid_kernel(const __grid_constant__ AugParams P) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];           // staged row band (+ halo rows)
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ ImgState st;
+    __shared__ float s_norm[TAB ? 768 : 1];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int band = blockIdx.x;
+    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
+    const uint32_t s_lo = P.geo[0].lo[band], s_len = P.geo[0].len[band];
+    if (TAB)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
+    wait_ticket(P.ready, P.ticket);
+    const int e0 = __ldcg(P.n_heavy), e1 = __ldcg(P.n_heavy + 1);
+    if ((int)blockIdx.y >= e1 - e0) return;                      // cluster-uniform
+    const int img = __ldcg(P.order + P.first + e0 + blockIdx.y);
+    const int idx = P.first + img;
+    if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)src_image(P, idx) * img_bytes + s_lo, s_len);
+    if (threadIdx.x < sizeof(Prog) / 4)
+        reinterpret_cast<uint32_t*>(&st.prog)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
+    __syncthreads();
+    if (P.chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied
+    if (s_len) mbar_wait(&s_bar, 0);
+
+    const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
+    const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
+    const size_t out_elem = OUT == OUT_F32 ? 4 : 2;
+    void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
+    const int cls = st.prog.cls;
+    const Ctx c = make_ctx(P, P.in + (size_t)src_image(P, idx) * img_bytes, s_dyn, s_lo, s_len, P.H, P.W, st, true);
+    const TailInfo t = make_tail(P, st.prog);
+    float* ftab = reinterpret_cast<float*>(&st.hist[0][0]);      // 768 floats; the slot-0 histogram is idle by then
+    if (cls == C_SHARP) {
+        const float alpha = bits_to_float(st.prog.op[0].a[0]);
+        const bool clip = st.prog.op[0].a[1] != 0;
+        if (st.prog.op[1].kind != K_NONE) {                      // static LUT partner: rides in the float table
+            make_lut((uint32_t)P.H * (uint32_t)P.W, st, 1, 0u);
+            build_ftab<TAB>(P, s_norm, st.lut[1], ftab);
+            if (clip) final_rows_sharp4<OUT, true, true>(P, ftab, c, alpha, t.flip, out_img, oy0, oy1);
+            else final_rows_sharp4<OUT, true, false>(P, ftab, c, alpha, t.flip, out_img, oy0, oy1);
+        } else {
+            if (clip) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+            else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        }
+    } else {                                                     // C_LUT with statistics
+        bool peers_pending = false;
+        if (scalar_stats_program(st.prog)) {
+            build_scalar_stats_table<TAB>(P, s_norm, st, c, y0, y1, cluster, ftab);
+            peers_pending = P.bands > 1;
+        } else {
+            prepare_image(P, c, y0, y1, st, cluster);
+            build_ftab<TAB>(P, s_norm, st.lutc, ftab);
+        }
+        const float pad[3] = {0.0f, 0.0f, 0.0f};                 // never used: there is no crop padding in this kernel
+        final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
+        if (peers_pending) cluster_wait();                       // peers have read this CTA's statistics record
+    }
+    zero_box_rows<OUT>(P, st.prog, out_img, oy0, oy1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1391,6 +1440,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     __shared__ __align__(16) uint8_t s_lut[2][768];
     __shared__ __align__(16) uint8_t s_lutc[768];
     __shared__ float s_ftab[OUT == OUT_U8_HWC ? 1 : 768];       // LUT programs: normalise(ch, lutc[ch][b])
+    __shared__ __align__(16) uint32_t s_tile[OUT == OUT_U8_HWC ? 4 : (kThreads / 32) * 128];   // affine gather tiles (128 px per warp)
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -1400,11 +1450,11 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
-    const int n_heavy = __ldcg(P.n_heavy);
+    const int n_heavy = __ldcg(P.n_heavy + 1);                  // entries in front of the light segment (heavy + mid)
     if ((int)blockIdx.y >= P.B - n_heavy) return;
     const int img = __ldcg(P.order + P.first + n_heavy + blockIdx.y);     // uniform load per warp
     const int idx = P.first + img;
-    if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)idx * img_bytes + s_lo, s_len);
+    if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)src_image(P, idx) * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
         reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
     __syncthreads();
@@ -1432,7 +1482,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
 
     const int cls = s_prog.cls;
     Ctx c;
-    c.raw = P.in + (size_t)idx * img_bytes; c.sraw = s_dyn; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u;
+    c.raw = P.in + (size_t)src_image(P, idx) * img_bytes; c.sraw = s_dyn; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u;
     c.H = P.H; c.W = P.W; c.rcp_w = P.rcp_w; c.rcp_wq = P.rcp_wq;
     if (cls == C_POINT || cls == C_GEOM) {
         c.op[0] = s_prog.op[0]; c.op[1] = s_prog.op[1]; c.box[0] = s_prog.box[0]; c.box[1] = s_prog.box[1];
@@ -1462,8 +1512,8 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
                         if (has_lut) final_rows_rowshift<OUT, true>(P, s_ftab, pad, c, rs, t.flip, out_img, oy0, oy1);
                         else final_rows_rowshift<OUT, TAB>(P, s_norm, pad, c, rs, t.flip, out_img, oy0, oy1);
                     } else {
-                        if (has_lut) final_rows_affine<OUT, true>(P, s_ftab, pad, c, gop, t.flip, out_img, oy0, oy1);
-                        else final_rows_affine<OUT, TAB>(P, s_norm, pad, c, gop, t.flip, out_img, oy0, oy1);
+                        if (has_lut) final_rows_affine<OUT, true>(P, s_ftab, pad, c, gop, t.flip, out_img, oy0, oy1, s_tile);
+                        else final_rows_affine<OUT, TAB>(P, s_norm, pad, c, gop, t.flip, out_img, oy0, oy1, s_tile);
                     }
                     done = true;
                 }
@@ -1480,8 +1530,8 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     }
     if (!done) {
         switch (cls) {
-        case C_PLAIN: final_rows_plain_lut<OUT, TAB, false>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
-        case C_LUT:   final_rows_plain_lut<OUT, TAB, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
+        case C_PLAIN: final_rows_plain_lut<OUT, TAB, false, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
+        case C_LUT:   final_rows_plain_lut<OUT, TAB, true, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
         case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
         default:      final_rows<OUT, TAB, C_GEOM, false>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
         }
@@ -1501,6 +1551,45 @@ __global__ void faa_mixup_kernel(const T* __restrict__ data, T* __restrict__ out
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per; i += (int64_t)gridDim.x * blockDim.x) {
         float x = (float)a[i], y = (float)p[i];
         o[i] = (T)f_add(f_mul(x, lam), f_mul(y, oml));
+    }
+}
+
+// 16-byte vectorised variant (n_per % VEC == 0, 16-byte aligned rows): the op is pure HBM streaming,
+// 2 reads + 1 write per element
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) faa_mixup_kernel_v(const T* __restrict__ data, T* __restrict__ out,
+                                                          const int64_t* __restrict__ perm, int64_t n_vec, int64_t n_per,
+                                                          float lam, float oml) {
+    const int b = blockIdx.y;
+    const uint4* a = reinterpret_cast<const uint4*>(data + (size_t)b * n_per);
+    const uint4* p = reinterpret_cast<const uint4*>(data + (size_t)perm[b] * n_per);
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)b * n_per);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 xa = __ldg(a + i), xp = __ldg(p + i);
+        uint4 r;
+        const uint32_t* ua = &xa.x; const uint32_t* up = &xp.x; uint32_t* ur = &r.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if constexpr (VEC == 4) {
+                ur[k] = __float_as_uint(f_add(f_mul(__uint_as_float(ua[k]), lam), f_mul(__uint_as_float(up[k]), oml)));
+            } else if constexpr (sizeof(T) == 2 && VEC == 8) {
+                float x0, x1, y0, y1;
+                if constexpr (std::is_same<T, __half>::value) {
+                    const float2 fx = __half22float2(*reinterpret_cast<const __half2*>(&ua[k]));
+                    const float2 fy = __half22float2(*reinterpret_cast<const __half2*>(&up[k]));
+                    x0 = fx.x; x1 = fx.y; y0 = fy.x; y1 = fy.y;
+                    const __half2 h = __floats2half2_rn(f_add(f_mul(x0, lam), f_mul(y0, oml)), f_add(f_mul(x1, lam), f_mul(y1, oml)));
+                    ur[k] = *reinterpret_cast<const uint32_t*>(&h);
+                } else {
+                    const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ua[k]));
+                    const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&up[k]));
+                    x0 = fx.x; x1 = fx.y; y0 = fy.x; y1 = fy.y;
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(f_add(f_mul(x0, lam), f_mul(y0, oml)), f_add(f_mul(x1, lam), f_mul(y1, oml)));
+                    ur[k] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+            }
+        }
+        o[i] = r;
     }
 }
 
@@ -1598,8 +1687,43 @@ static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
     return cudaLaunchKernelEx(&cfg, faa_augment_light_kernel<OUT, TAB>, p);
 }
 
+template <int OUT, bool TAB>
+static cudaError_t launch_mid(const AugParams& p, cudaStream_t stream) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        return cudaErrorInvalidValue;                            // the mid kernel writes float planes only
+    } else {
+        const size_t dyn = (size_t)p.geo[0].band_cap;
+        static size_t configured[kMaxDevices] = {};
+        int dev = 0;
+        if (cudaError_t e = cudaGetDevice(&dev)) return e;
+        if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+        if (dyn > configured[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(faa_augment_mid_kernel<OUT, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+            configured[dev] = dyn;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.bands;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = p.chain ? 2 : 1;
+        return cudaLaunchKernelEx(&cfg, faa_augment_mid_kernel<OUT, TAB>, p);
+    }
+}
+
 template <int OUT>
-cudaError_t launch_out(const AugParams& p, bool mix, bool tab, bool light, cudaStream_t stream) {
+cudaError_t launch_out(const AugParams& p, bool mix, bool tab, int which, cudaStream_t stream) {
+    const bool light = which == 1;
+    if (which == 2) return tab ? launch_mid<OUT, true>(p, stream) : launch_mid<OUT, false>(p, stream);
     if (light) return tab ? launch_light<OUT, true>(p, stream) : launch_light<OUT, false>(p, stream);
     if constexpr (OUT != OUT_U8_HWC) {                   // fused Mixup needs a float output
         if (mix) return tab ? launch_one<OUT, 2, true>(p, stream) : launch_one<OUT, 2, false>(p, stream);
@@ -1608,23 +1732,24 @@ cudaError_t launch_out(const AugParams& p, bool mix, bool tab, bool light, cudaS
 }
 
 #ifdef FAA_TU_OUT
-template cudaError_t launch_out<FAA_TU_OUT>(const AugParams&, bool, bool, bool, cudaStream_t);
+template cudaError_t launch_out<FAA_TU_OUT>(const AugParams&, bool, bool, int, cudaStream_t);
 #else
-extern template cudaError_t launch_out<OUT_F16>(const AugParams&, bool, bool, bool, cudaStream_t);
-extern template cudaError_t launch_out<OUT_BF16>(const AugParams&, bool, bool, bool, cudaStream_t);
-extern template cudaError_t launch_out<OUT_F32>(const AugParams&, bool, bool, bool, cudaStream_t);
-extern template cudaError_t launch_out<OUT_U8_HWC>(const AugParams&, bool, bool, bool, cudaStream_t);
+extern template cudaError_t launch_out<OUT_F16>(const AugParams&, bool, bool, int, cudaStream_t);
+extern template cudaError_t launch_out<OUT_BF16>(const AugParams&, bool, bool, int, cudaStream_t);
+extern template cudaError_t launch_out<OUT_F32>(const AugParams&, bool, bool, int, cudaStream_t);
+extern template cudaError_t launch_out<OUT_U8_HWC>(const AugParams&, bool, bool, int, cudaStream_t);
 
-// light == false: the cluster kernel (all images, or the heavy part of a split launch);
-// light == true : the streaming kernel for the light part of a split launch (p.n_heavy != nullptr)
-cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, bool light, cudaStream_t stream) {
+// which == 0: the cluster kernel (all images, or the heavy part of a split launch);
+// which == 1: the streaming kernel for the light part of a split launch (p.n_heavy != nullptr);
+// which == 2: the statistics / Sharpness kernel for the mid part of a three-way split
+cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, int which, cudaStream_t stream) {
     if (p.B <= 0) return cudaSuccess;
     const bool mix = p.partner != nullptr;
     switch (out_type) {
-    case OUT_F16:  return launch_out<OUT_F16>(p, mix, use_tab, light, stream);
-    case OUT_BF16: return launch_out<OUT_BF16>(p, mix, use_tab, light, stream);
-    case OUT_F32:  return launch_out<OUT_F32>(p, mix, true, light, stream);
-    case OUT_U8_HWC: return launch_out<OUT_U8_HWC>(p, false, false, light, stream);
+    case OUT_F16:  return launch_out<OUT_F16>(p, mix, use_tab, which, stream);
+    case OUT_BF16: return launch_out<OUT_BF16>(p, mix, use_tab, which, stream);
+    case OUT_F32:  return launch_out<OUT_F32>(p, mix, true, which, stream);
+    case OUT_U8_HWC: return launch_out<OUT_U8_HWC>(p, false, false, which, stream);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -1647,6 +1772,20 @@ cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream) {
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,
                          int dtype, float lam, float oml, cudaStream_t stream) {
     if (batch <= 0 || n_per_sample <= 0) return cudaSuccess;
+    const int vec = dtype == OUT_F32 ? 4 : 8;
+    if (n_per_sample % vec == 0 && ((uintptr_t)data % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+        const int64_t n_vec = n_per_sample / vec;
+        unsigned gv = (unsigned)((n_vec + 255) / 256);
+        if (gv > 32) gv = 32;
+        dim3 gridv(gv, (unsigned)batch, 1);
+        switch (dtype) {
+        case OUT_F16:  faa_mixup_kernel_v<__half, 8><<<gridv, 256, 0, stream>>>((const __half*)data, (__half*)out, perm, n_vec, n_per_sample, lam, oml); break;
+        case OUT_BF16: faa_mixup_kernel_v<__nv_bfloat16, 8><<<gridv, 256, 0, stream>>>((const __nv_bfloat16*)data, (__nv_bfloat16*)out, perm, n_vec, n_per_sample, lam, oml); break;
+        case OUT_F32:  faa_mixup_kernel_v<float, 4><<<gridv, 256, 0, stream>>>((const float*)data, (float*)out, perm, n_vec, n_per_sample, lam, oml); break;
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     unsigned gx = (unsigned)((n_per_sample + 255) / 256);
     if (gx > 64) gx = 64;
     dim3 grid(gx, (unsigned)batch, 1);

@@ -16,8 +16,8 @@ struct ResolveParams {
     const Box* boxes;           // [n][n_op] (may be nullptr when no Cutout box is needed)
     Prog* progs;                // [n] out
     int32_t* order;             // [n] out: local image indices, most expensive first (optional)
-    int32_t* n_heavy;           // out: number of leading order entries that need the cluster kernel (optional)
-    int32_t split;              // sort light programs behind heavy ones (two pixel launches)
+    int32_t* n_heavy;           // out (optional): [0] = end of the heavy segment of the order, [1] = end of the mid segment
+    int32_t split;              // 1: sort light programs behind heavy ones (two pixel launches); 2: heavy | mid | light
     Sample* samples_out;        // optional [n]
     Box* boxes_out;             // optional [n][n_op]
     RngCfg rng;
@@ -46,11 +46,13 @@ struct AugParams {
     const Prog* progs;          // [n_all]
     const int32_t* partner;     // [B] index into [0, n_all) or nullptr (no mixup)
     const int32_t* order;       // [n_all] LPT schedule written by the resolve kernel, or nullptr
-    const int32_t* n_heavy;     // device counter: schedule entries [0, n_heavy) -> cluster kernel, rest -> light kernel; nullptr = no split
+    const int32_t* n_heavy;     // device counters: schedule entries [0, n_heavy[0]) -> cluster kernel, [n_heavy[0], n_heavy[1]) -> mid
+                                // kernel (empty in a two-way split), rest -> light kernel; nullptr = no split
     const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values
     uint8_t* scratch;           // [n_all][H][W][3] uint8 scratch image for Sharpness->gather programs, or nullptr
     int32_t B, H, W, out_h, out_w;
     int32_t first;              // index of this launch's image 0 inside the n_all arrays
+    int32_t in_mod;             // > 0: replicated launch (TTA): entry v reads input image v % in_mod
     int32_t use_zero_box;
     int32_t bands;              // CTAs (== cluster size) per image of the cluster kernel (== geo[0].bands)
     BandGeom geo[2];            // [0] cluster kernel, [1] light streaming kernel
@@ -70,7 +72,7 @@ struct AugParams {
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };
-cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, bool light, cudaStream_t stream);
+cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, int which, cudaStream_t stream);   // which: 0 cluster, 1 light, 2 mid
 
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,
                          int dtype, float lam, float one_minus_lam, cudaStream_t stream);

@@ -7,17 +7,24 @@ rank-local under DDP, ``train.py:55``; global pairing is an extension):
 
 * the pairing and lambda are derived from a shared seed, identically on every rank (no
   communication);
-* ranks all-gather their **raw uint8** shards (3 B/px: half of the fp16 output, a quarter of the
-  fp32 one) - mixing is linear, so "augment the partner here" equals "augment there, send, mix";
-* the fused-Mixup kernel recomputes each partner's augmentation from the gathered raw image with
-  the partner's own decisions (Philox keyed by the *global* sample index, or gathered records).
+* every sample's partner is needed by exactly ONE sample (the pairing is a permutation), so the exchange
+  is a **partner-only all-to-all** of raw uint8 images (``mixup_global``): a rank receives only the <= B/G
+  images its own samples pair with - 1/G of what a whole-pool all-gather (``mixup_global_allgather``, kept
+  as the north star's baseline) would deliver - 3 B/px on the wire: half of the fp16 output, a quarter of fp32.
+  Mixing is linear, so "augment the partner here" equals "augment there, send, mix";
+* the fused-Mixup kernel recomputes each partner's augmentation from the received raw image with the
+  partner's own decisions: Philox records drawn for the GLOBAL sample indices on every rank (16 + 8 n_op
+  bytes per sample, no communication) and gathered into pool order.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .engine import CompiledPolicy, TailSpec, augment_batch, make_rng
 
 
@@ -55,9 +62,101 @@ def gather_pool(local: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def partner_plan(perm: torch.Tensor, rank: int, world: int):
+    """The partner-only exchange for the global pairing ``perm`` (contiguous equal shards), computed locally on
+    every rank.  Returns ``(send_idx, send_counts, recv_counts, partner_pool, recv_global)``:
+
+    * ``send_idx``     local indices of the images this rank sends, grouped by destination rank (within a
+      group in the order of the destination's samples), ``send_counts[r]`` of them go to rank r;
+    * ``recv_counts``  how many images arrive from each rank; they land, grouped by source rank, behind the
+      local shard in the pool ``[local shard | received]``;
+    * ``partner_pool`` for every local sample the pool index of its partner (a local index when the partner is
+      in this rank's own shard - nothing is sent to oneself);
+    * ``recv_global``  the global sample index of every received image (for its decision records)."""
+    n = int(perm.numel())
+    b = n // world
+    perm = perm.to(torch.int64).cpu()
+    owner = perm // b                                           # rank that owns each sample's partner
+    lo = rank * b
+    send_idx, send_counts = [], []
+    for r in range(world):                                      # what rank r's samples need from my shard
+        pr = perm[r * b:(r + 1) * b]
+        mine = pr[(owner[r * b:(r + 1) * b] == rank)] if r != rank else pr[:0]
+        send_idx.append(mine - lo)
+        send_counts.append(int(mine.numel()))
+    my_p, my_owner = perm[lo:lo + b], owner[lo:lo + b]
+    partner_pool = torch.empty(b, dtype=torch.int64)
+    recv_counts, recv_global = [], []
+    base = b
+    for s in range(world):                                      # received block of source rank s: my samples in order
+        sel = (my_owner == s).nonzero(as_tuple=True)[0]
+        if s == rank:
+            partner_pool[sel] = my_p[sel] - lo
+            recv_counts.append(0)
+            continue
+        partner_pool[sel] = base + torch.arange(sel.numel(), dtype=torch.int64)
+        recv_counts.append(int(sel.numel()))
+        recv_global.append(my_p[sel])
+        base += int(sel.numel())
+    return (torch.cat(send_idx) if send_idx else torch.empty(0, dtype=torch.int64), send_counts, recv_counts,
+            partner_pool, torch.cat(recv_global) if recv_global else torch.empty(0, dtype=torch.int64))
+
+
+def exchange_partners(local: torch.Tensor, send_idx, send_counts, recv_counts, group=None) -> torch.Tensor:
+    """All-to-all of the planned rows of ``local`` (dim 0); returns the received rows grouped by source rank."""
+    send = local.index_select(0, send_idx.to(local.device))
+    out = torch.empty((sum(recv_counts),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_to_all_single(out, send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=group)
+    return out
+
+
+def philox_records(policy: CompiledPolicy, n: int, h: int, w: int, tail: TailSpec, seed: int, first_index: int, device):
+    """Decision records of samples [first_index, first_index + n) drawn by the device sampler: uint8 tensors
+    ``(samples [n,16], boxes [n, 8*n_op])`` - what the fused Philox path would use for those indices."""
+    t = tail.c_struct(h, w)
+    rng = make_rng(seed, first_index, tail)
+    d_s = torch.zeros((n, 16), dtype=torch.uint8, device=device)
+    d_b = torch.zeros((n, 8 * policy.n_op), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib.faa_sample_philox(policy.handle, n, h, w, C.byref(t), C.byref(rng), d_s.data_ptr(), d_b.data_ptr(),
+                                              C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return d_s, d_b
+
+
 def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
-                 seed: int, step: int, group=None, samples=None, boxes=None):
-    """Augment this rank's shard and mix every sample with its partner from the GLOBAL batch.
+                 seed: int, step: int, group=None, timing=None):
+    """Augment this rank's shard and mix every sample with its partner from the GLOBAL batch; partners travel
+    by a partner-only all-to-all of raw uint8 images (module doc).  Returns ``(data, targets, partner_targets,
+    lam)`` like reference ``mixup`` (aug_mixup.py:23).  ``timing``: optional dict, receives CUDA events
+    ``ex0``/``ex1`` around the exchange and ``recv_bytes``."""
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    b, h, w = local_u8.shape[0], local_u8.shape[1], local_u8.shape[2]
+    n = b * world
+    dev = local_u8.device
+    perm, lam = global_pairing(n, alpha, seed, step)
+    lo, _ = shard_bounds(n, rank, world)
+    send_idx, send_counts, recv_counts, partner_pool, recv_global = partner_plan(perm, rank, world)
+    if timing is not None:
+        timing["ex0"] = torch.cuda.Event(enable_timing=True); timing["ex0"].record()
+    recv = exchange_partners(local_u8, send_idx, send_counts, recv_counts, group) if world > 1 else local_u8[:0]
+    all_targets = gather_pool(targets, group) if world > 1 else targets
+    if timing is not None:
+        timing["ex1"] = torch.cuda.Event(enable_timing=True); timing["ex1"].record()
+        timing["recv_bytes"] = int(recv.numel())
+    pool = torch.cat([local_u8, recv]) if recv.shape[0] else local_u8
+    # decisions: the device sampler's records of the global batch, in pool order
+    rec_s, rec_b = philox_records(policy, n, h, w, tail, seed, step * n, dev)
+    ids = torch.cat([torch.arange(lo, lo + b, dtype=torch.int64), recv_global]).to(dev)
+    pool_s, pool_b = rec_s.index_select(0, ids).reshape(-1), rec_b.index_select(0, ids).reshape(-1)
+    data = augment_batch(policy, local_u8, tail, partner=partner_pool, lam=lam, pool=pool, pool_samples=pool_s,
+                         pool_boxes=pool_b, first=0)
+    return data, targets, all_targets[perm[lo:lo + b].to(all_targets.device)], lam
+
+
+def mixup_global_allgather(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
+                           seed: int, step: int, group=None, samples=None, boxes=None):
+    """The north star's baseline exchange: all-gather of the WHOLE raw pool (G times the bytes ``mixup_global``
+    moves), then the same fused kernel.  Same results as ``mixup_global``.
 
     Returns ``(data, targets, partner_targets, lam)`` like reference ``mixup`` (aug_mixup.py:23).
     Decisions: fused Philox keyed by the global sample index (default), or resolved records given

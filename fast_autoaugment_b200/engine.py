@@ -75,9 +75,11 @@ class CompiledPolicy:
         subs = [list(s) for s in policies]
         if not subs:
             raise IndexError("Cannot choose from an empty sequence")       # random.choice on []
-        n_op = max(len(s) for s in subs)
-        if any(len(s) != n_op for s in subs):
-            raise ValueError("all sub-policies must have the same number of ops")
+        n_op = max(max(len(s) for s in subs), 1)
+        # ragged sub-policies (the reference's Augmentation accepts them): short ones are padded with slots that never
+        # fire (probability -1) and draw nothing - `pad[s][j]` marks them for the parity sampler
+        self.pad = np.array([[j >= len(s) for j in range(n_op)] for s in subs], dtype=bool)
+        subs = [s + [("Invert", -1.0, 0.0)] * (n_op - len(s)) for s in subs]
         self.policies = subs
         self.n_sub, self.n_op = len(subs), n_op
         self.names = [[str(op[0]) for op in s] for s in subs]
@@ -137,10 +139,15 @@ class CompiledPolicy:
         if crop_rng_h < 1 or crop_rng_w < 1:
             raise ValueError("Required crop size %s is larger than input image size %s" %
                              ((oh, ow), (h + 2 * tail.crop_pad, w + 2 * tail.crop_pad)))
+        if do_crop and (tail.crop_pad > 127 or crop_rng_h - 1 - tail.crop_pad > 127 or crop_rng_w - 1 - tail.crop_pad > 127):
+            raise _lib.FaaRuntimeError("RandomCrop offsets beyond +-127 pixels are not supported (int8 records): "
+                                       "crop on the host side")
         for i in range(batch):
             sub = random.choice(subs_range)                       # data.py:259
             gate = sign = 0
             for j in range(self.n_op):
+                if self.pad[sub, j]:                              # padding of a ragged sub-policy: no op, no draw
+                    continue
                 if random.random() > self.probs[sub, j]:          # data.py:261
                     continue
                 gate |= 1 << j
@@ -313,8 +320,49 @@ class FusedAugmenter:
         return torch.empty((batch,) + tuple(self.out_shape[1:]), dtype=self.tail.out_dtype, device=device)
 
     def __call__(self, batch_u8: torch.Tensor, out: torch.Tensor, first_index: int = 0, stream=None):
+        b = batch_u8.shape[0]
+        if (batch_u8.dtype != torch.uint8 or not batch_u8.is_cuda or not batch_u8.is_contiguous()
+                or tuple(batch_u8.shape[1:]) != (self.h, self.w, 3)):
+            raise ValueError("batch must be a contiguous uint8 CUDA tensor [B, %d, %d, 3]" % (self.h, self.w))
+        if (out.dtype != self.tail.out_dtype or out.device != batch_u8.device or not out.is_contiguous()
+                or tuple(out.shape) != (b,) + tuple(self.out_shape[1:])):
+            raise ValueError("out must be a contiguous %s tensor %s on %s" % (self.tail.out_dtype, (b,) + tuple(self.out_shape[1:]),
+                                                                             batch_u8.device))
         self.rng.first_index = first_index
-        s = stream if stream is not None else torch.cuda.current_stream(batch_u8.device).cuda_stream
-        check(lib.faa_augment(self.policy.handle, batch_u8.data_ptr(), out.data_ptr(), batch_u8.shape[0], self.h,
-                              self.w, self._t_ref, None, None, self._rng_ref, 0, C.c_void_p(s)))
+        dev = batch_u8.device
+        s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        if dev.index == torch.cuda.current_device():
+            check(lib.faa_augment(self.policy.handle, batch_u8.data_ptr(), out.data_ptr(), b, self.h,
+                                  self.w, self._t_ref, None, None, self._rng_ref, 0, C.c_void_p(s)))
+        else:
+            with torch.cuda.device(dev):
+                check(lib.faa_augment(self.policy.handle, batch_u8.data_ptr(), out.data_ptr(), b, self.h,
+                                      self.w, self._t_ref, None, None, self._rng_ref, 0, C.c_void_p(s)))
         return out
+
+
+def augment_tta(policy: CompiledPolicy, batch_u8: torch.Tensor, tail: TailSpec, replicas: int, seed: int, first_index: int = 0,
+                out=None):
+    """Test-time-augmentation batching for the policy search (reference search.py:87-125): the reference builds
+    ``num_policy`` validation loaders that each augment the SAME validation batch with their own random draws and then
+    reduces the per-sample losses over the replicas.  Here ONE launch produces all replicas:
+
+        out[r] == augment_batch(policy, batch_u8, tail, rng=make_rng(seed, first_index + r * B, tail))
+
+    uint8 [B,H,W,3] CUDA batch -> [replicas, B, 3, out_h, out_w] (or [replicas, B, out_h, out_w, 3] uint8)."""
+    _require_cuda(batch_u8, "batch")
+    if batch_u8.dtype != torch.uint8 or batch_u8.dim() != 4 or batch_u8.shape[-1] != 3:
+        raise ValueError("batch must be uint8 [B, H, W, 3]")
+    batch_u8 = batch_u8.contiguous()
+    B, H, W, _ = batch_u8.shape
+    t = tail.c_struct(H, W)
+    shape = (replicas, B, t.out_h, t.out_w, 3) if tail.out_dtype == torch.uint8 else (replicas, B, 3, t.out_h, t.out_w)
+    if out is None:
+        out = torch.empty(shape, dtype=tail.out_dtype, device=batch_u8.device)
+    elif tuple(out.shape) != shape or out.dtype != tail.out_dtype or not out.is_contiguous():
+        raise ValueError("out has the wrong shape/dtype")
+    rng = make_rng(seed, first_index, tail)
+    with torch.cuda.device(batch_u8.device):
+        check(lib.faa_augment_tta(policy.handle, batch_u8.data_ptr(), out.data_ptr(), B, int(replicas), H, W, C.byref(t),
+                                  C.byref(rng), _stream_ptr(batch_u8.device)))
+    return out

@@ -161,6 +161,15 @@ int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int f
                       const faa_rng_t* rng, const int32_t* d_partner, float lam, float one_minus_lam,
                       void* stream);
 
+/* ---- test-time-augmentation batching: replaces the `num_policy` validation loaders of
+ * eval_tta (search.py:87-90: one get_dataloaders call per replica, each drawing its own
+ * sub-policies for the SAME validation batch, the losses reduced per sample at :116-125).
+ * ONE launch augments d_in [batch] `replicas` times: d_out [replicas][batch][3][out_h][out_w];
+ * replica r uses the decisions of global samples rng->first_index + r*batch + i, i.e. it equals
+ * faa_augment called with first_index + r*batch.  Policies of at most FAA_MAX_FUSED_OPS ops. */
+int faa_augment_tta(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, int replicas,
+                    int h, int w, const faa_tail_t* tail, const faa_rng_t* rng, void* stream);
+
 /* same call with HOST buffers: pinned staging, chunked H2D / kernel / D2H pipeline inside.
  * h_out may be NULL (result stays on the device in d_out_keep, which may also be NULL). */
 int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_out_keep,

@@ -14,7 +14,7 @@ import torch
 
 from helpers import ALL_OPS, ROOT, seed_all
 
-from fast_autoaugment_b200 import _lib, archive
+from fast_autoaugment_b200 import _lib, archive, engine
 from fast_autoaugment_b200.engine import CompiledPolicy, TailSpec
 from oracle import np_model, pil_path
 
@@ -266,3 +266,117 @@ def test_philox_sampler_distributions(emu):
     emu.faa_emu_philox(table.ctypes.data, probs.ctypes.data, pol.n_sub, 2, C.byref(rng3), B, 32, 32, 32, 32,
                        s2.ctypes.data, b.ctypes.data)
     assert (s["sub"] == s2["sub"]).mean() < 0.01
+
+
+def _philox(emu, pol, tail, B, H, W, seed=7, first=0):
+    from fast_autoaugment_b200.engine import make_rng
+    rng = make_rng(seed, first, tail)
+    oh, ow = tail.out_size if tail.out_size is not None else (H, W)
+    table = np.ascontiguousarray(pol.compiled_table(H, W))
+    s = np.zeros(B, dtype=_lib.SAMPLE_DTYPE)
+    b = np.zeros((B, pol.n_op), dtype=_lib.BOX_DTYPE)
+    probs = np.ascontiguousarray(pol.probs)
+    emu.faa_emu_philox(table.ctypes.data, probs.ctypes.data, pol.n_sub, pol.n_op, C.byref(rng), B, H, W, oh, ow,
+                       s.ctypes.data, b.ctypes.data)
+    return s, b
+
+
+def test_philox_sampler_chi_square(emu):
+    """the production sampler's distributions against the reference's draws, by goodness of
+    fit instead of loose means - sub-policy choice (data.py:259), per-slot gates (data.py:261), mirror signs
+    (augmentations.py:15...), flips, crops and the Cutout centres with numpy's legacy uniform(w) = uniform(low=w,
+    high=1.0) quirk (augmentations.py:131-137).  The emulation runs the kernels' own source (faa_core.cuh)."""
+    from scipy import stats
+    pol = CompiledPolicy(archive.fa_reduced_cifar10())
+    tail = TailSpec.cifar(16)
+    B = 400000
+    s, b = _philox(emu, pol, tail, B, 32, 32)
+    # sub-policy: uniform over n_sub (random.choice)
+    counts = np.bincount(s["sub"], minlength=pol.n_sub)
+    assert stats.chisquare(counts).pvalue > 1e-4
+    # gates: for every (sub-policy, slot) the applied count is Binomial(n, prob): z-scores are standard normal
+    zs = []
+    for j in range(2):
+        applied = np.bincount(s["sub"], weights=((s["gate"] >> j) & 1), minlength=pol.n_sub)
+        p = pol.probs[:, j]
+        var = counts * p * (1 - p)
+        ok = var > 5
+        zs.append(((applied - counts * p)[ok]) / np.sqrt(var[ok]))
+        assert np.all(applied[p == 0.0] == 0) and np.all((applied == counts)[p == 1.0])
+    zs = np.concatenate(zs)
+    assert stats.kstest(zs, "norm").pvalue > 1e-4 and np.abs(zs).max() < 5.5
+    # mirror signs: fair coin for every applied mirrored op, nothing for the others
+    for j in range(2):
+        app = ((s["gate"] >> j) & 1) > 0
+        mir = pol.draw[s["sub"], j] == _lib.DRAW_MIRROR
+        sg = ((s["sign"] >> j) & 1)
+        k, n = int(sg[app & mir].sum()), int((app & mir).sum())
+        assert stats.binomtest(k, n, 0.5).pvalue > 1e-4
+        assert sg[~(app & mir)].sum() == 0
+    assert stats.binomtest(int(s["flip"].sum()), B, 0.5).pvalue > 1e-4
+    for f in ("crop_dy", "crop_dx"):                                   # torch.randint(0, 9) - 4
+        assert stats.chisquare(np.bincount(s[f].astype(int) + 4, minlength=9)).pvalue > 1e-4
+    for k in (0, 2):                                                   # CutoutDefault centres: np.random.randint(32)
+        lo = s["zero_box"][:, k].astype(int)
+        centre_like = np.bincount(np.clip(lo, 0, 31), minlength=32)
+        exp = np.full(32, B / 32.0); exp[0] = 9 * B / 32.0; exp[24:] = 0          # lo = clip(c - 8, 0, 32), c uniform in 0..31
+        assert stats.chisquare(centre_like[:24], exp[:24] * centre_like[:24].sum() / exp[:24].sum()).pvalue > 1e-4
+    # Cutout boxes: x0 = int(max(0, W + (1 - W) u - v/2)), numpy legacy uniform(low=W, high=1.0); inclusive box x0..int(min(W, x0+v))
+    j = 1
+    subs = [i for i in range(pol.n_sub) if pol.names[i][j] == "Cutout" and pol.levels[i, j] * 0.2 > 0][:3]
+    for sub in subs:
+        sel = (s["sub"] == sub) & (((s["gate"] >> j) & 1) > 0)
+        v = pol.levels[sub, j] * 0.2 * 32
+        x0 = b[sel, j]["x0"].astype(int)
+        u = np.random.default_rng(1).random(2_000_000)
+        ref = np.maximum(0, 32 + (1 - 32) * u - v / 2).astype(int)
+        exp = np.bincount(ref, minlength=33)[:33] / len(ref)
+        got = np.bincount(x0, minlength=33)[:33]
+        keep = exp * len(x0) > 5
+        assert got[~keep].sum() <= 5 + 5 * (~keep).sum()
+        assert stats.chisquare(got[keep], exp[keep] / exp[keep].sum() * got[keep].sum()).pvalue > 1e-4, sub
+        assert x0.min() >= 0 and (x0 == 0).mean() > 0                  # the quirk: centres never fall in [0, 1), boxes pile up at 0
+
+
+def test_philox_random_crop_uses_the_torchvision_range(emu):
+    """RandomCrop offsets come from [0, H + 2p - out_h] x [0, W + 2p - out_w] (torchvision get_params), also
+    when the output is smaller than the image; ranges that do not fit the int8 records are refused"""
+    from scipy import stats
+    pol = CompiledPolicy([[("Invert", 0.5, 0.0), ("Invert", 0.5, 0.0)]])
+    tail = TailSpec((24, 40), 2, True, engine.CIFAR_MEAN, engine.CIFAR_STD, 0, torch.float16)
+    s, _ = _philox(emu, pol, tail, 60000, 32, 48)
+    dy, dx = s["crop_dy"].astype(int), s["crop_dx"].astype(int)
+    assert dy.min() == -2 and dy.max() == 32 + 2 - 24 and dx.min() == -2 and dx.max() == 48 + 2 - 40
+    assert stats.chisquare(np.bincount(dy + 2)).pvalue > 1e-4 and stats.chisquare(np.bincount(dx + 2)).pvalue > 1e-4
+    big = TailSpec((224, 224), 0, True, engine.CIFAR_MEAN, engine.CIFAR_STD, 0, torch.float16)
+    with pytest.raises(_lib.FaaRuntimeError):
+        pol.sample_parity(2, 512, 512, big)                            # offsets up to 288: refused, not wrapped
+
+
+def test_ragged_sub_policies_replay_the_reference_draws():
+    """the reference's Augmentation accepts sub-policies of different lengths (data.py:259-263 just loops
+    over what is there); missing slots are padded with never-firing ops that consume no random number"""
+    policies = [[("Invert", 0.6, 0.5)], [("Rotate", 0.5, 0.3), ("Color", 0.7, 0.6)], [("ShearX", 0.9, 0.2), ("Cutout", 0.4, 0.5)], []]
+    pol = CompiledPolicy(policies)
+    assert pol.n_op == 2 and pol.pad.tolist() == [[False, True], [False, False], [False, False], [True, True]]
+    seed_all(5)
+    got, _ = pol.sample_parity(300, 32, 32)
+    seed_all(5)
+    for i in range(300):
+        sub = random.choice(range(len(policies)))
+        gate = sign = 0
+        for j, (name, pr, level) in enumerate(policies[sub]):
+            if random.random() > pr:
+                continue
+            gate |= 1 << j
+            if name in ("Rotate", "ShearX"):
+                sign |= (random.random() > 0.5) << j
+            elif name == "Cutout":
+                np.random.uniform(32); np.random.uniform(32)
+        assert (got[i]["sub"], got[i]["gate"], got[i]["sign"]) == (sub, gate, sign), i
+    # the C++ MT19937 replay agrees with the Python one
+    seed_all(6)
+    a, ab = pol.sample_parity(200, 32, 32)
+    seed_all(6)
+    c, cb, _, _ = pol.sample_policy_mt(200, 32, 32)
+    assert a[["sub", "gate", "sign"]].tobytes() == c[["sub", "gate", "sign"]].tobytes() and ab.tobytes() == cb.tobytes()

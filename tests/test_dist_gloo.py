@@ -57,6 +57,16 @@ def _worker(rank, world, port, out_dir):
     pool_b = gather_pool(x_b).numpy().reshape(-1).view(boxes.dtype).reshape(n, -1)
     assert pool_s.tobytes() == samples.tobytes() and pool_b.tobytes() == boxes.tobytes()
 
+    # partner-only exchange (BASELINE config 4): every rank receives exactly the raw images its samples pair with
+    from fast_autoaugment_b200.distributed import exchange_partners, partner_plan
+    send_idx, send_counts, recv_counts, partner_pool, recv_global = partner_plan(perm, rank, world)
+    assert send_counts[rank] == 0 and recv_counts[rank] == 0 and sum(recv_counts) <= b
+    recv = exchange_partners(torch.from_numpy(batch[lo:hi]), send_idx, send_counts, recv_counts)
+    pool2 = torch.cat([torch.from_numpy(batch[lo:hi]), recv])
+    assert torch.equal(pool2[partner_pool], torch.from_numpy(batch)[perm[lo:hi]])       # every partner is in the pool
+    assert torch.equal(torch.from_numpy(batch)[recv_global], recv)                      # ... under its global index
+    assert pool2.shape[0] == b + sum(recv_counts) < n                                    # less than the whole pool
+
     emu = set_emu_sigs(ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libfaa_emu.so")))
     norm = exact_norm_table(CIFAR_MEAN, CIFAR_STD)
     mine = emu_augment(emu, pol, batch[lo:hi], samples[lo:hi], boxes[lo:hi], tail, norm,

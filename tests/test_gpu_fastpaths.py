@@ -89,3 +89,26 @@ def test_octet_paths_match_oracle(shape, norm, split_min, monkeypatch):
         w = want[i].clone()
         w[:, zb[0]:zb[1], zb[2]:zb[3]] = 0
         assert torch.equal(got[i], w), (i, policies[i])
+
+
+@pytest.mark.parametrize("B,shape,replicas,dtype,cutout,split_min", [(64, (32, 32), 5, torch.float32, 16, "1000000000000"),
+                                                                     (96, (224, 224), 3, torch.float16, 0, "0"),
+                                                                     (40, (56, 104), 4, torch.uint8, 0, "1000000000000")])
+def test_tta_replicas_equal_single_launches(B, shape, replicas, dtype, cutout, split_min, monkeypatch):
+    """search.py:87-125 batching (row N4): ONE launch evaluates `num_policy` replicas of a validation batch; replica r must
+    equal the plain launch that draws the decisions of samples first_index + r*B + i (both schedules: cluster kernel
+    alone and the split kernels)"""
+    from fast_autoaugment_b200 import archive
+    from fast_autoaugment_b200.engine import augment_tta, make_rng
+    monkeypatch.setenv("FAA_SPLIT_MIN", split_min)
+    H, W = shape
+    pol = CompiledPolicy(archive.fa_reduced_cifar10() if H == 32 else archive.fa_resnet50_rimagenet())
+    tail = TailSpec.cifar(cutout, dtype) if H == 32 else (TailSpec.raw_u8() if dtype == torch.uint8 else TailSpec.imagenet(cutout, dtype))
+    x = torch.from_numpy(synth_batch(B, shape, seed=31)).cuda()
+    got = augment_tta(pol, x, tail, replicas, seed=9, first_index=1000)
+    assert got.shape[0] == replicas and got.shape[1] == B
+    ref_pol = CompiledPolicy(pol.policies)
+    for r in range(replicas):
+        want = augment_batch(ref_pol, x, tail, rng=make_rng(9, 1000 + r * B, tail))
+        assert torch.equal(got[r], want), r
+    assert not torch.equal(got[0], got[1])

@@ -38,6 +38,8 @@ for row in csv.reader(sys.stdin):
             cur["ops"][op[0].split(".")[0]] += ins
 # ncu prints one block per (result, file): merge consecutive blocks of the same function until the SASS repeats
 for i, r in enumerate(res):
+    if sum(r["lines"].values()) < 200000:
+        continue
     tot = sum(r["ops"].values()) or 1
     tl = sum(r["lines"].values()) or 1
     ts = sum(r["samp"].values()) or 1
