@@ -218,6 +218,7 @@ struct faa_policy {
     void* h_out_stage = nullptr; size_t h_out_bytes = 0;
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaStream_t light_stream = nullptr; cudaEvent_t ev_res = nullptr, ev_light = nullptr;
+    cudaStream_t mid_stream = nullptr; cudaEvent_t ev_mid = nullptr;   // the mid kernel of a three-way split co-runs on its own stream
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     cudaEvent_t ev_host_done = nullptr; bool host_in_flight = false;   // faa_augment_host: last call's work (it owns d_in / stages)
     std::mutex call_mu;                  // launches of one policy are serialised (speculation state, slots, staging)
@@ -328,6 +329,8 @@ int faa_policy_destroy(faa_policy_t* p) {
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_host_done) cudaEventDestroy(p->ev_host_done);
     if (p->light_stream) cudaStreamDestroy(p->light_stream);
+    if (p->mid_stream) cudaStreamDestroy(p->mid_stream);
+    if (p->ev_mid) cudaEventDestroy(p->ev_mid);
     if (p->ahead_stream) cudaStreamDestroy(p->ahead_stream);
     if (p->ev_ahead) cudaEventDestroy(p->ev_ahead);
     if (p->ev_res) cudaEventDestroy(p->ev_res);
@@ -682,12 +685,12 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC &&
                            (size_t)batch * h * w >= split_min;
     R.split = use_split ? 1 : 0;
-    // Chained steps (default for the fused-Philox production path): resolve(N+1), cluster(N), light(N) all on the
+    // Chained steps (FAA_CHAIN=1|2; off by default): resolve(N+1), cluster(N), mid(N), light(N) all on the
     // caller's stream with programmatic dependent launches, no events and no side streams.  Consecutive steps
     // overlap (the next step's CTAs fill the slots the previous step's tail frees); the only true dependency -
     // programs written by the resolve kernel - is a ticket word the pixel kernels poll.  FAA_CHAIN=0: the
     // two-stream schedule with events (light kernel on the caller's stream, cluster kernel on a priority stream).
-    int chain_mode = 1;
+    int chain_mode = 0;                                   // measured (profiles/r02_schedules.txt): the event schedule co-runs the kernels better
     if (const char* e = getenv("FAA_CHAIN")) chain_mode = atoi(e);
     const bool use_chain = chain_mode != 0 && use_split && allow_ahead && rng && !d_samples && !d_partner &&
                            !(getenv("FAA_AHEAD") && getenv("FAA_AHEAD")[0] == '0');
@@ -697,6 +700,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const bool use_mid = use_split && !mid_off && P.stage && (w & 3) == 0 && tail->out_w == w && tail->out_h == h &&
                          P.crop_pad == 0 && ((uintptr_t)d_out % 16) == 0;
     if (use_mid) R.split = 2;
+    if (use_split && P.octets && P.crop_pad == 0) R.allow |= 4;     // the lean gather paths exist in this launch
     // program / schedule buffers come in two slots; a slot = progs[cap] + order[cap] + counters[2 cap] + ready[cap]
     const size_t cap_imgs = p->d_progs_bytes / sizeof(Prog);
     auto bind_slot = [&](int slot, ResolveParams& r, AugParams* a) {
@@ -735,8 +739,8 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         memcpy(key.v, v, sizeof v);
     }
     auto set_mid_geometry = [&](AugParams& a) {
-        int mb = P.bands;                                   // halve the band count while a band (+ halo) stays <= 40 KB
-        while (mb > 1 && band_capacity(mb / 2, h, w, tail->out_h, 0) <= 40 * 1024) mb /= 2;
+        int mb = P.bands;                                   // halve the band count while a band (+ halo) stays <= 80 KB (2 CTAs / SM)
+        while (mb > 1 && band_capacity(mb / 2, h, w, tail->out_h, 0) <= 80 * 1024) mb /= 2;
         static const int mid_bands = [] { const char* e = getenv("FAA_MID_BANDS"); return e ? atoi(e) : 0; }();
         if (mid_bands >= 1 && mid_bands <= 8 && (mid_bands & (mid_bands - 1)) == 0 && mid_bands <= h) mb = mid_bands;
         a.bands = mb;
@@ -826,6 +830,12 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
                 CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
                 CK(cudaStreamCreateWithPriority(&p->ahead_stream, cudaStreamNonBlocking, hi));   // one block: get a slot promptly
             }
+            {
+                int lo = 0, hi = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CK(cudaStreamCreateWithPriority(&p->mid_stream, cudaStreamNonBlocking, hi));
+            }
+            CK(cudaEventCreateWithFlags(&p->ev_mid, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&p->ev_res, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&p->ev_light, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&p->ev_ahead, cudaEventDisableTiming));
@@ -865,10 +875,23 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         } else {
             AugParams Ph = P; Ph.pdl = 0;                           // not behind the resolve kernel in its stream
             CK(cudaStreamWaitEvent(p->light_stream, p->ev_res, 0));
-            CK(launch_augment(P, tail->out_dtype, use_tab, 1, stream));
+            static const bool mid_same = [] { const char* e = getenv("FAA_MID_STREAM"); return e && e[0] == '0'; }();
+            static const int order_knob = [] { const char* e = getenv("FAA_ORDER"); return e ? atoi(e) : 0; }();
+            if (use_mid && !mid_same) CK(cudaStreamWaitEvent(p->mid_stream, p->ev_res, 0));
+            // the streaming kernel goes FIRST: it fills the machine at once; the priority streams' clusters then take
+            // the slots its CTAs free (launched first, the thousands of exiting CTAs of the cluster kernels would hold
+            // up the work distributor: measured +10 us per step)
+            if (order_knob == 0) CK(launch_augment(P, tail->out_dtype, use_tab, 1, stream));
             CK(launch_augment(Ph, tail->out_dtype, use_tab, 0, p->light_stream));
-            if (use_mid) { AugParams Pm = Ph; set_mid_geometry(Pm); CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, p->light_stream)); g_launches++; }
+            if (order_knob == 1) CK(launch_augment(P, tail->out_dtype, use_tab, 1, stream));
+            if (use_mid) {                                                               // statistics / Sharpness clusters: third stream
+                AugParams Pm = Ph; set_mid_geometry(Pm);
+                CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, mid_same ? p->light_stream : p->mid_stream)); g_launches++;
+                if (!mid_same) CK(cudaEventRecord(p->ev_mid, p->mid_stream));
+            }
+            if (order_knob == 2) CK(launch_augment(P, tail->out_dtype, use_tab, 1, stream));
             CK(cudaEventRecord(p->ev_light, p->light_stream));
+            if (use_mid && !mid_same) CK(cudaStreamWaitEvent(stream, p->ev_mid, 0));
         }
         CK(cudaStreamWaitEvent(stream, p->ev_light, 0));
         g_launches += 2;

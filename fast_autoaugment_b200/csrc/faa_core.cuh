@@ -464,8 +464,10 @@ enum ProgClass : uint8_t {
     C_GEOM = 6,      // one geometric op + pointwise ops: incremental fixed-point source coordinates
     C_SG = 7,        // Sharpness then a geometric op: the sharpened image goes through a global scratch
                      // image (L2-resident), then the gather reads it - no 9-tap re-evaluation per gather
-    C_MAT = 5        // op0 then (Sharpness | statistics op): op0's output is materialised chunk-wise in
+    C_MAT = 5,       // op0 then (Sharpness | statistics op): op0's output is materialised chunk-wise in
                      // shared memory and op1 runs on it as a single-op program of class `cls2`
+    C_GEOM2 = 8      // two geometric ops (launches with the lean gather paths only): the two nearest-neighbour
+                     // coordinate maps compose per pixel - no intermediate image
 };
 
 struct alignas(16) Prog {   // 96 bytes (moved with 128-bit loads / stores)
@@ -483,7 +485,8 @@ FAA_HD bool kind_is_lutlike(int k) { return k == K_NONE || kind_uses_lut(k); }
 
 // Sample + boxes -> Prog.  ops: compiled table [n_sub][n_op][2]; boxes: this sample's n_op boxes.
 // allow: bit 0 = the launch has a materialisation chunk of at least 3 rows, bit 1 = it has a global
-// scratch image (both only for single-source launches).
+// scratch image (both only for single-source launches), bit 2 = split launch with the lean gather paths
+// (float planes of the image's own size, W % 8 == 0, no crop).
 FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, int n_op, int op_base,
                        int apply_tail, int H, int W, int out_w, int allow, Prog& g) {
     const bool allow_mat = (allow & 1) != 0, allow_scratch = (allow & 2) != 0;
@@ -534,6 +537,7 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
         g.cls = C_SG;
     } else if (((k0 == K_AFFINE || k0 == K_SHIFT) && kind_is_pointwise(k1)) ||
                ((k1 == K_AFFINE || k1 == K_SHIFT) && kind_is_pointwise(k0))) g.cls = C_GEOM;
+    else if ((allow & 4) && (k0 == K_AFFINE || k0 == K_SHIFT) && (k1 == K_AFFINE || k1 == K_SHIFT)) g.cls = C_GEOM2;
     else if (!aligned) g.cls = C_GENERIC;
     else if (all_point) g.cls = n == 0 ? C_PLAIN : all_lut ? C_LUT : C_POINT;
     else if (k0 == K_SHARPNESS && kind_is_pointwise(k1)) g.cls = C_SHARP;
@@ -543,15 +547,18 @@ FAA_HD void build_prog(const Sample& s_in, const Box* boxes, const OpRec* ops, i
 // "Light" programs need no whole-image statistics and no neighbourhood: they run in the small
 // streaming kernel (no cluster, few registers); everything else runs in the cluster kernel.
 FAA_HD bool prog_is_light(const Prog& g) {
-    return g.stat_mask == 0 && (g.cls == C_PLAIN || g.cls == C_LUT || g.cls == C_POINT || g.cls == C_GEOM);
+    return g.stat_mask == 0 && (g.cls == C_PLAIN || g.cls == C_LUT || g.cls == C_POINT || g.cls == C_GEOM || g.cls == C_GEOM2);
 }
 
 // "Mid" programs: whole-image statistics feeding per-channel LUTs, or Sharpness (+ a static LUT) - they need a
 // cluster (statistics exchange) or only halo rows, but none of the cluster kernel's materialisation / generic
 // machinery: they run in their own lean kernel when the launch geometry allows it (three-way split).
-FAA_HD bool prog_is_mid(const Prog& g) {
-    const int k1 = g.op[1].kind;
+FAA_HD bool prog_is_mid(const Prog& g, int allow) {
+    const int k0 = g.op[0].kind, k1 = g.op[1].kind;
     if (g.cls == C_LUT) return g.stat_mask != 0;
+    // statistics LUT, then a gather: the table rides through the lean gather paths (fill colour = plain zero)
+    if (g.cls == C_GEOM) return (allow & 4) && g.stat_mask == 1 && (k0 == K_AUTOCONTRAST || k0 == K_EQUALIZE || k0 == K_CONTRAST) &&
+                                (k1 == K_AFFINE || k1 == K_SHIFT);
     return g.cls == C_SHARP && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
 }
 

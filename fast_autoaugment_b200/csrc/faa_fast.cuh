@@ -74,9 +74,10 @@ __device__ __forceinline__ bool rowshift_of(const OpRec& r, RowShift& rs) {
 
 // USE_TAB: value = tab[ch][byte] (LUT partner composed with the normalisation, or the exact table);
 // pad[ch]: the normalised fill value for pixels whose source is outside the image
-template <int OUT, bool USE_TAB>
+template <int OUT, bool USE_TAB, bool FLIP>
 __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
-                                                    const RowShift rs, int flip, void* out_img, int oy0, int oy1) {
+                                                    const RowShift rs, void* out_img, int oy0, int oy1) {
+    constexpr int flip = FLIP ? 1 : 0;
     using T = typename OutElem<OUT>::T;
     const int W = P.W, H = P.H;
     const uint32_t opr = (uint32_t)W >> 3;
@@ -99,10 +100,12 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
             fill_oct<OUT>(o, plane, pad);                                 // nothing of the octet has a source
         } else if (s0 == s7) {
             // One shift for the whole octet: its sources are 24 contiguous bytes from byte B0 of the image.  At a
-            // row edge only pixels [lo, hi) of the octet have a source; the aligned words are then clamped into the
-            // source row (valid memory, ignored bytes) and the missing pixels take the fill value.
+            // row edge only pixels [lo, hi) of the octet have a source; the aligned words are always clamped into the
+            // source row (valid memory, ignored bytes), and warps that hold an edge octet patch the missing pixels
+            // with the fill value after the normalisation - full and edge octets share one instruction stream.
             const int lo = max(0, -sx0), hi = min(8, W - sx0);
-            const uint32_t vmask = (0xFFu >> (8 - hi)) & (0xFFu << lo) & 0xFFu;
+            uint32_t vmask = (0xFFu >> (8 - hi)) & (0xFFu << lo) & 0xFFu;
+            if (flip) vmask = __brev(vmask) >> 24;
             const int row_lo = ys * (int)pitch, row_hi = row_lo + (int)pitch - 4;
             const int B0 = row_lo + sx0 * 3, A = B0 & ~3;
             const uint32_t k = (uint32_t)B0 & 3u;
@@ -119,15 +122,24 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
             uint32_t w[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) w[j] = __funnelshift_r(v[j], v[j + 1], 8u * k);
-            if (vmask == 0xFFu) {
-                if (flip) stream_oct<OUT, USE_TAB, true>(P, w, tab, o, plane);
-                else stream_oct<OUT, USE_TAB, false>(P, w, tab, o, plane);
-            } else {
-                uint32_t q[8], px[8];
-                unpack12(w[0], w[1], w[2], q); unpack12(w[3], w[4], w[5], q + 4);
+            const bool patch = __any_sync(__activemask(), vmask != 0xFFu);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) px[j] = flip ? q[7 - j] : q[j];
-                emit_oct_masked<OUT, USE_TAB>(P, tab, o, plane, px, flip ? (__brev(vmask) >> 24) : vmask, pad);
+            for (int ch = 0; ch < 3; ++ch) {
+                uint32_t u[8]; float nv[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int bi = 3 * kk + ch;                          // byte of source pixel kk
+                    u[kk] = (w[bi >> 2] >> (8 * (bi & 3))) & 255u;
+                }
+                float fv[8];
+                norm8<USE_TAB>(P, tab, ch, u, fv);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) nv[kk] = fv[FLIP ? 7 - kk : kk];
+                if (patch) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) nv[kk] = ((vmask >> kk) & 1u) ? nv[kk] : pad[ch];
+                }
+                store_plane8<OUT>(o + ch * plane, nv);
             }
         } else {
             // a shift break (Pillow's accumulated float offset) inside the octet: per pixel
@@ -148,50 +160,78 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------
-// General affine gather (ShearY, Rotate).  Sources come from global memory (L1): a rotated band has no compact
+// General gather (ShearY, Rotate; two geometric ops).  Sources come from global memory (L1): a rotated band has no compact
 // source footprint.  To keep the gather coalesced each warp works on a tile of 128 consecutive output pixels in two
 // phases: (1) lane l fetches pixels l, l+32, l+64, l+96 of the tile - neighbouring lanes read neighbouring source
 // pixels, two aligned word loads and a funnel shift each - into a shared-memory tile; (2) lane l normalises pixels
 // 4l..4l+3 and writes 8-byte plane quads.  `tile`: 128 words per warp.
-template <int OUT, bool USE_TAB>
-__device__ __forceinline__ void final_rows_affine(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
-                                                  const OpRec op, int flip, void* out_img, int oy0, int oy1, uint32_t* tile) {
+// one nearest-neighbour coordinate map (Pillow affine_fixed / unit-scale ImagingScaleAffine, faa_core.cuh Level::at)
+__device__ __forceinline__ bool map_xy(const OpRec& o, int& x, int& y, int W, int H) {
+    int xin, yin;
+    if (o.kind == K_AFFINE) { xin = (o.a[2] + o.a[0] * x + o.a[1] * y) >> 16; yin = (o.a[5] + o.a[3] * x + o.a[4] * y) >> 16; }
+    else { xin = x + o.a[0] + (x >= o.a[2]); yin = y + o.a[1] + (y >= o.a[3]); }
+    x = xin; y = yin;
+    return (unsigned)xin < (unsigned)W && (unsigned)yin < (unsigned)H;
+}
+
+// one source pixel (24 bits) of the gather, bit 24 set when it exists.  opA maps the output pixel into the image in
+// front of it; opB (may be null) maps that position into the image in front of opB.  Both records live in shared memory.
+__device__ __forceinline__ uint32_t gather_fetch(const uint8_t* raw, int W, int H, const OpRec* opA, const OpRec* opB, int x, int y) {
+    bool ok = map_xy(*opA, x, y, W, H);
+    if (opB != nullptr) { const bool ok2 = map_xy(*opB, x, y, W, H); ok = ok && ok2; }      // CTA-uniform
+    const uint32_t off = ok ? (uint32_t)(y * W + x) * 3u : 0u;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + (off & ~3u));
+    const uint32_t lo = __ldg(wp);
+    const uint32_t hi = (off & 2u) ? __ldg(wp + 1) : 0u;                 // bytes 2,3 of the word: the pixel spills into the next one
+    const uint32_t px = __funnelshift_r(lo, hi, 8u * (off & 3u)) & 0xFFFFFFu;
+    return ok ? (px | 0x01000000u) : 0u;
+}
+
+template <int OUT, bool USE_TAB, bool FULL>
+__device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
+                                                    const OpRec* opA, const OpRec* opB, int flip, void* out_img, int oy0, int oy1,
+                                                    uint32_t* tile) {
     using T = typename OutElem<OUT>::T;
     const int W = P.W, H = P.H;
     const uint32_t npx = (uint32_t)(oy1 - oy0) * (uint32_t)W;
     const uint32_t plane = (uint32_t)H * (uint32_t)W;
     T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
-    const int a0 = op.a[0], a1 = op.a[1], a2 = op.a[2], a3 = op.a[3], a4 = op.a[4], a5 = op.a[5];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     uint32_t* my = tile + warp * 128u;
     const uint8_t* raw = c.raw;
     FastDiv dw; dw.init((uint32_t)W, P.rcp_w);
     for (uint32_t base = warp * 128u; base < npx; base += nwarp * 128u) {
+        if (W >= 32) {                                                   // one division per tile, then x += 32 with at most one wrap
+            const uint32_t p = base + lane;
+            const uint32_t r = dw.div(p);
+            int x = (int)(p - r * (uint32_t)W), y = oy0 + (int)r;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t p = base + lane + 32u * (uint32_t)i;
-            uint32_t v = 0u;
-            if (p < npx) {
-                const uint32_t r = dw.div(p);
-                const int x = (int)(p - r * (uint32_t)W), y = oy0 + (int)r;
-                const int ax = flip ? W - 1 - x : x;
-                const int xs = (a2 + a0 * ax + a1 * y) >> 16, ys = (a5 + a3 * ax + a4 * y) >> 16;
-                const bool ok = (unsigned)xs < (unsigned)W && (unsigned)ys < (unsigned)H;
-                const uint32_t off = ok ? (uint32_t)(ys * W + xs) * 3u : 0u;
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + (off & ~3u));
-                const uint32_t lo = __ldg(wp);
-                const uint32_t hi = (off & 2u) ? __ldg(wp + 1) : 0u;     // bytes 2,3 of the word: the pixel spills into the next one
-                const uint32_t px = __funnelshift_r(lo, hi, 8u * (off & 3u)) & 0xFFFFFFu;
-                v = ok ? (px | 0x01000000u) : 0u;                        // bit 24: the pixel has a source
+            for (int i = 0; i < 4; ++i) {
+                uint32_t v = 0u;
+                if (FULL || p + 32u * (uint32_t)i < npx) v = gather_fetch(raw, W, H, opA, opB, flip ? W - 1 - x : x, y);
+                my[lane + 32u * (uint32_t)i] = v;
+                x += 32;
+                if (x >= W) { x -= W; ++y; }
             }
-            my[lane + 32u * (uint32_t)i] = v;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t p = base + lane + 32u * (uint32_t)i;
+                uint32_t v = 0u;
+                if (p < npx) {
+                    const uint32_t r = dw.div(p);
+                    const int x = (int)(p - r * (uint32_t)W);
+                    v = gather_fetch(raw, W, H, opA, opB, flip ? W - 1 - x : x, oy0 + (int)r);
+                }
+                my[lane + 32u * (uint32_t)i] = v;
+            }
         }
         __syncwarp();
         const uint32_t p0 = base + 4u * lane;
-        if (p0 < npx) {
+        if (FULL || p0 < npx) {
             const uint4 q4 = reinterpret_cast<const uint4*>(my)[lane];
             const uint32_t px[4] = {q4.x, q4.y, q4.z, q4.w};
-            const uint32_t valid = (q4.x >> 24) | ((q4.y >> 24) << 1) | ((q4.z >> 24) << 2) | ((q4.w >> 24) << 3);
+            const bool patch = __any_sync(__activemask(), ((q4.x & q4.y & q4.z & q4.w) >> 24) == 0u);
             T* o = dst + p0;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
@@ -205,15 +245,24 @@ __device__ __forceinline__ void final_rows_affine(const AugParams& P, const floa
                     const float2 r1 = __ffma2_rn(make_float2((float)((px[2] >> (8 * ch)) & 255u), (float)((px[3] >> (8 * ch)) & 255u)), sc, bi);
                     v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
                 }
-                if (valid != 15u) {
+                if (patch) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) v[k] = ((valid >> k) & 1u) ? v[k] : pad[ch];
+                    for (int k = 0; k < 4; ++k) v[k] = (px[k] >> 24) ? v[k] : pad[ch];
                 }
                 store_plane4<OUT>(o + ch * plane, v, true, 4);
             }
         }
         __syncwarp();
     }
+}
+
+template <int OUT, bool USE_TAB>
+__device__ __forceinline__ void final_rows_gather(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
+                                                  const OpRec* opA, const OpRec* opB, int flip, void* out_img, int oy0, int oy1,
+                                                  uint32_t* tile) {
+    const uint32_t npx = (uint32_t)(oy1 - oy0) * (uint32_t)P.W;
+    if ((npx & 127u) == 0u) final_rows_gather_t<OUT, USE_TAB, true>(P, tab, pad, c, opA, opB, flip, out_img, oy0, oy1, tile);
+    else final_rows_gather_t<OUT, USE_TAB, false>(P, tab, pad, c, opA, opB, flip, out_img, oy0, oy1, tile);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -340,6 +389,28 @@ __device__ __forceinline__ void final_rows_cutout(const AugParams& P, const floa
 __device__ __forceinline__ uint32_t pair_lo(uint32_t w) { return __byte_perm(w, 0u, 0x4140); }   // (b0, b1) as 16-bit lanes
 __device__ __forceinline__ uint32_t pair_hi(uint32_t w) { return __byte_perm(w, 0u, 0x4342); }   // (b2, b3)
 
+// zb[12]: kBias15 + byte of the quad in source order -> normalised plane quads (FLIP: mirrored)
+template <int OUT, bool USE_TAB, bool FLIP>
+__device__ __forceinline__ void sharp_emit(const AugParams& P, const float* tab, const float zb[12], typename OutElem<OUT>::T* o,
+                                           uint32_t plane) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float v[4];
+        if (USE_TAB) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = tab[ch * 256 + (__float_as_uint(zb[3 * (FLIP ? 3 - k : k) + ch]) & 255u)];
+        } else {
+            const float2 nk = make_float2(-kBias15, -kBias15);
+            const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
+            const float2 a = __fadd2_rn(make_float2(zb[3 * (FLIP ? 3 : 0) + ch], zb[3 * (FLIP ? 2 : 1) + ch]), nk);
+            const float2 b = __fadd2_rn(make_float2(zb[3 * (FLIP ? 1 : 2) + ch], zb[3 * (FLIP ? 0 : 3) + ch]), nk);
+            const float2 r0 = __ffma2_rn(a, sc, bi), r1 = __ffma2_rn(b, sc, bi);
+            v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
+        }
+        store_plane4<OUT>(o + ch * plane, v, true, 4);
+    }
+}
+
 template <int OUT, bool USE_TAB, bool CLIP>
 __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const float* tab, const Ctx& c, float alpha, int flip,
                                                   void* out_img, int oy0, int oy1) {
@@ -388,19 +459,22 @@ __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const floa
             for (int m = 2; m < 8; ++m) {                                 // output bytes 2m-4, 2m-3
                 const uint32_t t = sh[m - 2] + colp[m] + sh[m + 1];      // col[k-3] + col[k] + col[k+3]
                 const uint32_t x2 = 2u * t + 8u * ctr[m] + 0x000D000Du;  // 2 S + 13 per lane (< 6644)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = 2 * m + h;                             // byte index from byte -4
-                    const float fx = __uint_as_float(__byte_perm(x2, kBias15Bits, h ? 0x7632 : 0x7610));    // kBias15 + (2S+13)
-                    const float u = fmaf(__fadd_rn(fx, -kBias15), k26, h26);        // (2S+13+.5)/26: never within 0.019 of an integer
-                    const float fdeg = __fadd_rz(u, kBias15);                       // kBias15 + floor(u)
-                    const float fctr = biased_byte(wb[k >> 2], k & 3);
-                    const float d = __fadd_rn(fctr, -fdeg);                         // (float)(px - deg), exact
-                    const float tt = __fadd_rn(__fadd_rn(fdeg, -kBias15), __fmul_rn(alpha, d));   // Blend.c
-                    float z = __fadd_rz(tt, kBias15);
-                    if (CLIP) z = fminf(fmaxf(z, kBias15), kBias15 + 255.0f);
-                    zb[k - 4] = z;
+                // the two bytes of the pair as packed fp32x2 (sm_100 FADD2 / FMUL2 / FFMA2: half the issue slots)
+                const int k0 = 2 * m, k1 = 2 * m + 1;                    // byte indices from byte -4
+                const float2 kk = make_float2(kBias15, kBias15), nk = make_float2(-kBias15, -kBias15);
+                const float2 fx = make_float2(__uint_as_float(__byte_perm(x2, kBias15Bits, 0x7610)),
+                                              __uint_as_float(__byte_perm(x2, kBias15Bits, 0x7632)));    // kBias15 + (2S+13)
+                const float2 u = __ffma2_rn(__fadd2_rn(fx, nk), make_float2(k26, k26), make_float2(h26, h26));   // (2S+13+.5)/26
+                const float2 fdeg = __fadd2_rz(u, kk);                                                  // kBias15 + floor(u)
+                const float2 fctr = make_float2(biased_byte(wb[k0 >> 2], k0 & 3), biased_byte(wb[k1 >> 2], k1 & 3));
+                const float2 d = __ffma2_rn(fdeg, make_float2(-1.0f, -1.0f), fctr);                    // (float)(px - deg), exact
+                const float2 tt = __fadd2_rn(__fadd2_rn(fdeg, nk), __fmul2_rn(make_float2(alpha, alpha), d));   // Blend.c, no contraction
+                float2 z = __fadd2_rz(tt, kk);
+                if (CLIP) {
+                    z.x = fminf(fmaxf(z.x, kBias15), kBias15 + 255.0f);
+                    z.y = fminf(fmaxf(z.y, kBias15), kBias15 + 255.0f);
                 }
+                zb[k0 - 4] = z.x; zb[k1 - 4] = z.y;
             }
             // first / last pixel of the row are image border: copied
             if (!has_l) {
@@ -413,22 +487,8 @@ __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const floa
             }
         }
         T* o = dst + 4u * q;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float zz = zb[3 * k + ch];
-                v[k] = USE_TAB ? tab[ch * 256 + (__float_as_uint(zz) & 255u)] : __fadd_rn(zz, -kBias15);
-            }
-            if (flip) { float t0 = v[0], t1 = v[1]; v[0] = v[3]; v[1] = v[2]; v[2] = t1; v[3] = t0; }
-            if (!USE_TAB) {
-                const float2 sc = make_float2(P.scale[ch], P.scale[ch]), bi = make_float2(P.bias[ch], P.bias[ch]);
-                const float2 r0 = __ffma2_rn(make_float2(v[0], v[1]), sc, bi), r1 = __ffma2_rn(make_float2(v[2], v[3]), sc, bi);
-                v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
-            }
-            store_plane4<OUT>(o + ch * plane, v, true, 4);
-        }
+        if (flip) sharp_emit<OUT, USE_TAB, true>(P, tab, zb, o, plane);
+        else sharp_emit<OUT, USE_TAB, false>(P, tab, zb, o, plane);
         qx += dxq; r += dr;
         if (qx >= qpr) { qx -= qpr; ++r; }
     }

@@ -59,7 +59,7 @@ struct __align__(16) ImgState {
     uint32_t xpart[8];          // scalar statistics of this CTA's band (read remotely through DSMEM): per-channel
                                 // min [0..2], max [3..5] (AutoContrast) or the luma sum [6] lo, [7] hi (Contrast)
     uint32_t xtot[8];           // ... reduced over the cluster
-    uint32_t wred[8][8];        // per-warp partials
+    uint32_t wred[16][8];       // per-warp partials (up to 512 threads)
 };
 
 struct FastDiv {
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
             Prog g;
             build_prog(s, bx, P.ops, P.n_op, P.op_base, P.apply_tail, P.H, P.W, P.out_w, P.allow, g);
             // weight class: 0 heavy (cluster kernel), 1 mid (statistics / Sharpness kernel, three-way split only), 2 light
-            const int wc = !P.split ? 0 : prog_is_light(g) ? 2 : (P.split == 2 && prog_is_mid(g)) ? 1 : 0;
+            const int wc = !P.split ? 0 : prog_is_light(g) ? 2 : (P.split == 2 && prog_is_mid(g, P.allow)) ? 1 : 0;
             g.bucket = (uint8_t)(cost_bucket(prog_cost(g)) + wc * kCostBuckets);
             P.progs[i] = g;
             atomicAdd(&s_count[g.bucket], 1);
@@ -163,6 +163,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                      : "=r"(ok) : "r"(b), "r"(phase) : "memory");
     }
 }
+
+// schedule words (order / counters / programs) are written by the resolve kernel: in the event-ordered schedule that
+// kernel has completed (read-only cache is fine); in the chained schedule it may have run concurrently with earlier
+// CTAs of this SM, so the loads bypass L1
+__device__ __forceinline__ int ld_sched(const int32_t* p, int chain) { return chain ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ uint32_t ld_sched(const uint32_t* p, int chain) { return chain ? __ldcg(p) : __ldg(p); }
 
 // TTA replicas (search.py:87-125): schedule entry v of a replicated launch augments input image v % in_mod with
 // its own decisions; in_mod == 0: one input image per entry
@@ -1149,8 +1155,8 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 
 __device__ __forceinline__ bool scalar_stats_program(const Prog& g) {
     const int k0 = g.op[0].kind, k1 = g.op[1].kind;
-    return g.cls == C_LUT && (k0 == K_AUTOCONTRAST || k0 == K_CONTRAST) &&
-           (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
+    return (g.cls == C_LUT || g.cls == C_GEOM) && (k0 == K_AUTOCONTRAST || k0 == K_CONTRAST) &&
+           (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS || k1 == K_AFFINE || k1 == K_SHIFT);
 }
 
 // returns with ftab / st.lutc complete (barrier included); the caller must call cluster_wait() once more before
@@ -1281,9 +1287,9 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     wait_ticket(P.ready, P.ticket);
 
     // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule
-    if (P.n_heavy != nullptr && (int)blockIdx.y >= __ldcg(P.n_heavy)) return;      // cluster-uniform
+    if (P.n_heavy != nullptr && (int)blockIdx.y >= ld_sched(P.n_heavy, P.chain)) return;      // cluster-uniform
     // LPT schedule entry: a uniform load per warp (no shared-memory hand-off, no barrier)
-    const int img = P.order ? __ldcg(P.order + P.first + blockIdx.y) : (int)blockIdx.y;
+    const int img = P.order ? ld_sched(P.order + P.first + blockIdx.y, P.chain) : (int)blockIdx.y;
     int src_idx[NSRC];
     src_idx[0] = P.first + img;
     if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
@@ -1299,7 +1305,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     for (int s = 0; s < NSRC; ++s)
         if (threadIdx.x < sizeof(Prog) / 4)
             reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
-                __ldcg(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x);
+                ld_sched(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x, P.chain);
     __syncthreads();
     // chained steps: the next kernel of the stream may start once every CTA of this one has copied its program
     // (it may overwrite the OTHER program slot only); Sharpness->gather programs also own a scratch image that
@@ -1365,12 +1371,14 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
 // histogram path for Equalize and pushed-forward histograms, the byte-stream Sharpness, the streaming final pass.
 // Preconditions (host, three-way split only): float output of the image's own size, no crop, W % 4 == 0, staged bands.
 // It owns schedule entries [n_heavy[0], n_heavy[1]).
+constexpr int kMidThreadsMax = 512;     // two tall bands per image, 512 threads each: 2 CTAs / SM at 224x224
 template <int OUT, bool TAB>
-__global__ void __launch_bounds__(kThreads, 4) faa_augment_mid_kernel(const __grid_constant__ AugParams P) {
+__global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(const __grid_constant__ AugParams P) {
     extern __shared__ __align__(128) uint8_t s_dyn[];           // staged row band (+ halo rows)
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st;
     __shared__ float s_norm[TAB ? 768 : 1];
+    __shared__ __align__(16) uint32_t s_tile[(kMidThreadsMax / 32) * 128];      // gather tiles (128 px per warp)
     __shared__ __align__(8) uint64_t s_bar;
 
     const int band = blockIdx.x;
@@ -1379,13 +1387,13 @@ __global__ void __launch_bounds__(kThreads, 4) faa_augment_mid_kernel(const __gr
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
-    const int e0 = __ldcg(P.n_heavy), e1 = __ldcg(P.n_heavy + 1);
+    const int e0 = ld_sched(P.n_heavy, P.chain), e1 = ld_sched(P.n_heavy + 1, P.chain);
     if ((int)blockIdx.y >= e1 - e0) return;                      // cluster-uniform
-    const int img = __ldcg(P.order + P.first + e0 + blockIdx.y);
+    const int img = ld_sched(P.order + P.first + e0 + blockIdx.y, P.chain);
     const int idx = P.first + img;
     if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)src_image(P, idx) * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
-        reinterpret_cast<uint32_t*>(&st.prog)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
+        reinterpret_cast<uint32_t*>(&st.prog)[threadIdx.x] = ld_sched(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x, P.chain);
     __syncthreads();
     if (P.chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied
     if (s_len) mbar_wait(&s_bar, 0);
@@ -1417,10 +1425,23 @@ __global__ void __launch_bounds__(kThreads, 4) faa_augment_mid_kernel(const __gr
             peers_pending = P.bands > 1;
         } else {
             prepare_image(P, c, y0, y1, st, cluster);
-            build_ftab<TAB>(P, s_norm, st.lutc, ftab);
+            if (cls == C_LUT) build_ftab<TAB>(P, s_norm, st.lutc, ftab);
         }
-        const float pad[3] = {0.0f, 0.0f, 0.0f};                 // never used: there is no crop padding in this kernel
-        final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
+        if (cls == C_GEOM) {
+            // statistics LUT then a gather: the LUT ran BEFORE the gather, so pixels without a source are plain zero
+            if (!scalar_stats_program(st.prog)) build_ftab<TAB>(P, s_norm, st.lut[0], ftab);      // (not a C_LUT program: no composed lutc)
+            const float pad[3] = {normalise<TAB>(P, s_norm, 0, 0u), normalise<TAB>(P, s_norm, 1, 0u), normalise<TAB>(P, s_norm, 2, 0u)};
+            RowShift rs;
+            if (rowshift_of(st.prog.op[1], rs)) {
+                if (t.flip) final_rows_rowshift<OUT, true, true>(P, ftab, pad, c, rs, out_img, oy0, oy1);
+                else final_rows_rowshift<OUT, true, false>(P, ftab, pad, c, rs, out_img, oy0, oy1);
+            } else {
+                final_rows_gather<OUT, true>(P, ftab, pad, c, &st.prog.op[1], nullptr, t.flip, out_img, oy0, oy1, s_tile);
+            }
+        } else {
+            const float pad[3] = {0.0f, 0.0f, 0.0f};             // never used: there is no crop padding in this kernel
+            final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
+        }
         if (peers_pending) cluster_wait();                       // peers have read this CTA's statistics record
     }
     zero_box_rows<OUT>(P, st.prog, out_img, oy0, oy1);
@@ -1450,13 +1471,13 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     if (TAB)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
-    const int n_heavy = __ldcg(P.n_heavy + 1);                  // entries in front of the light segment (heavy + mid)
+    const int n_heavy = ld_sched(P.n_heavy + 1, P.chain);       // entries in front of the light segment (heavy + mid)
     if ((int)blockIdx.y >= P.B - n_heavy) return;
-    const int img = __ldcg(P.order + P.first + n_heavy + blockIdx.y);     // uniform load per warp
+    const int img = ld_sched(P.order + P.first + n_heavy + blockIdx.y, P.chain);     // uniform load per warp
     const int idx = P.first + img;
     if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)src_image(P, idx) * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
-        reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x);
+        reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = ld_sched(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x, P.chain);
     __syncthreads();
     if (P.chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied: see the cluster kernel
     const uint32_t lut_mask = s_prog.lut_mask;
@@ -1484,7 +1505,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     Ctx c;
     c.raw = P.in + (size_t)src_image(P, idx) * img_bytes; c.sraw = s_dyn; c.s_lo = s_lo; c.s_len2 = s_len > 2u ? s_len - 2u : 0u;
     c.H = P.H; c.W = P.W; c.rcp_w = P.rcp_w; c.rcp_wq = P.rcp_wq;
-    if (cls == C_POINT || cls == C_GEOM) {
+    if (cls == C_POINT || cls == C_GEOM || cls == C_GEOM2) {
         c.op[0] = s_prog.op[0]; c.op[1] = s_prog.op[1]; c.box[0] = s_prog.box[0]; c.box[1] = s_prog.box[1];
     }
     c.lut[0] = s_lut[0]; c.lut[1] = s_lut[1];
@@ -1495,9 +1516,14 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     bool done = false;
     if constexpr (OUT != OUT_U8_HWC) {
         // lean octet paths (faa_fast.cuh) for the common geometry; everything else takes the generic evaluators
-        if ((cls == C_GEOM || cls == C_POINT) && octet_geometry(P, t) && band_fully_staged(c, t, oy0, oy1)) {
+        if ((cls == C_GEOM || cls == C_POINT || cls == C_GEOM2) && octet_geometry(P, t) && band_fully_staged(c, t, oy0, oy1)) {
             const int k0 = s_prog.op[0].kind, k1 = s_prog.op[1].kind;
-            if (cls == C_GEOM) {
+            if (cls == C_GEOM2) {
+                // two gathers: out(x) = raw(map0(map1(x))), zero wherever either map leaves the image
+                const float pad[3] = {normalise<TAB>(P, s_norm, 0, 0u), normalise<TAB>(P, s_norm, 1, 0u), normalise<TAB>(P, s_norm, 2, 0u)};
+                final_rows_gather<OUT, TAB>(P, s_norm, pad, c, &s_prog.op[1], &s_prog.op[0], t.flip, out_img, oy0, oy1, s_tile);
+                done = true;
+            } else if (cls == C_GEOM) {
                 const bool g0 = k0 == K_AFFINE || k0 == K_SHIFT;          // geometric op first, partner after it
                 const int pk = g0 ? k1 : k0;
                 if (pk == K_NONE || kind_uses_lut(pk)) {
@@ -1509,11 +1535,17 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
                         pad[ch] = (has_lut && g0) ? s_ftab[ch * 256] : normalise<TAB>(P, s_norm, ch, 0u);
                     RowShift rs;
                     if (rowshift_of(gop, rs)) {
-                        if (has_lut) final_rows_rowshift<OUT, true>(P, s_ftab, pad, c, rs, t.flip, out_img, oy0, oy1);
-                        else final_rows_rowshift<OUT, TAB>(P, s_norm, pad, c, rs, t.flip, out_img, oy0, oy1);
+                        if (has_lut) {
+                            if (t.flip) final_rows_rowshift<OUT, true, true>(P, s_ftab, pad, c, rs, out_img, oy0, oy1);
+                            else final_rows_rowshift<OUT, true, false>(P, s_ftab, pad, c, rs, out_img, oy0, oy1);
+                        } else {
+                            if (t.flip) final_rows_rowshift<OUT, TAB, true>(P, s_norm, pad, c, rs, out_img, oy0, oy1);
+                            else final_rows_rowshift<OUT, TAB, false>(P, s_norm, pad, c, rs, out_img, oy0, oy1);
+                        }
                     } else {
-                        if (has_lut) final_rows_affine<OUT, true>(P, s_ftab, pad, c, gop, t.flip, out_img, oy0, oy1, s_tile);
-                        else final_rows_affine<OUT, TAB>(P, s_norm, pad, c, gop, t.flip, out_img, oy0, oy1, s_tile);
+                        const OpRec* gp = g0 ? &s_prog.op[0] : &s_prog.op[1];
+                        if (has_lut) final_rows_gather<OUT, true>(P, s_ftab, pad, c, gp, nullptr, t.flip, out_img, oy0, oy1, s_tile);
+                        else final_rows_gather<OUT, TAB>(P, s_norm, pad, c, gp, nullptr, t.flip, out_img, oy0, oy1, s_tile);
                     }
                     done = true;
                 }
@@ -1533,6 +1565,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
         case C_PLAIN: final_rows_plain_lut<OUT, TAB, false, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
         case C_LUT:   final_rows_plain_lut<OUT, TAB, true, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
         case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
+        case C_GEOM2: final_rows<OUT, TAB, C_GENERIC>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
         default:      final_rows<OUT, TAB, C_GEOM, false>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
         }
     }
@@ -1703,8 +1736,12 @@ static cudaError_t launch_mid(const AugParams& p, cudaStream_t stream) {
             configured[dev] = dyn;
         }
         cudaLaunchConfig_t cfg = {};
+        static const int mid_threads = [] { const char* e = getenv("FAA_MID_THREADS"); int v = e ? atoi(e) : 0;
+                                            return (v == 128 || v == 256 || v == 512) ? v : 0; }();
+        // enough threads for the band: 512 for the tall bands of large images, 256 otherwise
+        const int threads = mid_threads ? mid_threads : ((size_t)p.geo[0].band_cap > 48 * 1024 ? 512 : 256);
         cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
-        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.blockDim = dim3((unsigned)threads, 1, 1);
         cfg.dynamicSmemBytes = dyn;
         cfg.stream = stream;
         cudaLaunchAttribute attr[2];

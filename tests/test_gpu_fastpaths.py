@@ -39,6 +39,7 @@ def _policies():
         for g in ("ShearX", "Rotate", "TranslateY"):
             pols.append([(a, 1.0, rng.random()), (g, 1.0, rng.random())])
             pols.append([(g, 1.0, rng.random()), (a, 1.0, rng.random())])
+    pols += [[(a, 1.0, rng.random()), (b, 1.0, rng.random())] for a in ALL_OPS for b in ALL_OPS]   # every ordered pair
     pols += [[("Color", 1.0, rng.random()), (l, 1.0, rng.random())] for l in LUTS]
     pols += [[("Cutout", 1.0, rng.random()), ("Color", 1.0, rng.random())], [("Color", 1.0, 0.3), ("Color", 1.0, 0.9)],
              [("Invert", 1.0, 0.3), ("Solarize", 1.0, 0.4)], [("AutoContrast", 1.0, 0.3), ("ShearX", 1.0, 0.9)],

@@ -1,5 +1,4 @@
 #!/bin/bash
-# the bench mix under the scheduling switches (each line: env -> us/step)
-for e in "FAA_CHAIN=1" "FAA_CHAIN=2" "FAA_CHAIN=0" "FAA_CHAIN=1 FAA_MID=0" "FAA_CHAIN=0 FAA_MID=0" "FAA_CHAIN=1 FAA_MID_BANDS=8" "FAA_CHAIN=1 FAA_MID_BANDS=2"; do
+for e in "FAA_X=0" "FAA_ORDER=1" "FAA_ORDER=2" "FAA_MID_BANDS=4 FAA_MID_THREADS=256" "FAA_MID_BANDS=4 FAA_MID_THREADS=256 FAA_MID_STREAM=0" "FAA_MID_STREAM=0" "FAA_CHAIN=1"; do
   env $e python tools/mix_probe.py
 done
