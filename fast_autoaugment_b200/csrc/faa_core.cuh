@@ -559,6 +559,8 @@ FAA_HD bool prog_is_mid(const Prog& g, int allow) {
     // statistics LUT, then a gather: the table rides through the lean gather paths (fill colour = plain zero)
     if (g.cls == C_GEOM) return (allow & 4) && g.stat_mask == 1 && (k0 == K_AUTOCONTRAST || k0 == K_EQUALIZE || k0 == K_CONTRAST) &&
                                 (k1 == K_AFFINE || k1 == K_SHIFT);
+    // per-channel LUT (static or from statistics) or Color, then Sharpness: op0 is applied in place to the staged band
+    if (g.cls == C_MAT) return g.cls2 == C_SHARP && k1 == K_SHARPNESS && (kind_uses_lut(k0) || k0 == K_COLOR);
     return g.cls == C_SHARP && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
 }
 

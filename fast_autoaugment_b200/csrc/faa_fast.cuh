@@ -166,19 +166,25 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
 // pixels, two aligned word loads and a funnel shift each - into a shared-memory tile; (2) lane l normalises pixels
 // 4l..4l+3 and writes 8-byte plane quads.  `tile`: 128 words per warp.
 // one nearest-neighbour coordinate map (Pillow affine_fixed / unit-scale ImagingScaleAffine, faa_core.cuh Level::at)
-__device__ __forceinline__ bool map_xy(const OpRec& o, int& x, int& y, int W, int H) {
+// with its six parameters in registers: K_AFFINE 16.16 coefficients, or K_SHIFT dx, dy, bx, by in a0..a3
+struct MapRegs { int aff, a0, a1, a2, a3, a4, a5; };
+__device__ __forceinline__ MapRegs map_regs(const OpRec& o) {
+    MapRegs m; m.aff = o.kind == K_AFFINE; m.a0 = o.a[0]; m.a1 = o.a[1]; m.a2 = o.a[2]; m.a3 = o.a[3]; m.a4 = o.a[4]; m.a5 = o.a[5];
+    return m;
+}
+__device__ __forceinline__ bool map_xy(const MapRegs& m, int& x, int& y, int W, int H) {
     int xin, yin;
-    if (o.kind == K_AFFINE) { xin = (o.a[2] + o.a[0] * x + o.a[1] * y) >> 16; yin = (o.a[5] + o.a[3] * x + o.a[4] * y) >> 16; }
-    else { xin = x + o.a[0] + (x >= o.a[2]); yin = y + o.a[1] + (y >= o.a[3]); }
+    if (m.aff) { xin = (m.a2 + m.a0 * x + m.a1 * y) >> 16; yin = (m.a5 + m.a3 * x + m.a4 * y) >> 16; }
+    else { xin = x + m.a0 + (x >= m.a2); yin = y + m.a1 + (y >= m.a3); }
     x = xin; y = yin;
     return (unsigned)xin < (unsigned)W && (unsigned)yin < (unsigned)H;
 }
 
-// one source pixel (24 bits) of the gather, bit 24 set when it exists.  opA maps the output pixel into the image in
-// front of it; opB (may be null) maps that position into the image in front of opB.  Both records live in shared memory.
-__device__ __forceinline__ uint32_t gather_fetch(const uint8_t* raw, int W, int H, const OpRec* opA, const OpRec* opB, int x, int y) {
-    bool ok = map_xy(*opA, x, y, W, H);
-    if (opB != nullptr) { const bool ok2 = map_xy(*opB, x, y, W, H); ok = ok && ok2; }      // CTA-uniform
+// one source pixel (24 bits) of the gather, bit 24 set when it exists.  mA maps the output pixel into the image in
+// front of the last op; opB (shared memory, may be null: CTA-uniform) maps that position into the image in front of it.
+__device__ __forceinline__ uint32_t gather_fetch(const uint8_t* raw, int W, int H, const MapRegs& mA, const OpRec* opB, int x, int y) {
+    bool ok = map_xy(mA, x, y, W, H);
+    if (opB != nullptr) { const MapRegs mB = map_regs(*opB); const bool ok2 = map_xy(mB, x, y, W, H); ok = ok && ok2; }
     const uint32_t off = ok ? (uint32_t)(y * W + x) * 3u : 0u;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + (off & ~3u));
     const uint32_t lo = __ldg(wp);
@@ -199,6 +205,7 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     uint32_t* my = tile + warp * 128u;
     const uint8_t* raw = c.raw;
+    const MapRegs mA = map_regs(*opA);
     FastDiv dw; dw.init((uint32_t)W, P.rcp_w);
     for (uint32_t base = warp * 128u; base < npx; base += nwarp * 128u) {
         if (W >= 32) {                                                   // one division per tile, then x += 32 with at most one wrap
@@ -208,7 +215,7 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint32_t v = 0u;
-                if (FULL || p + 32u * (uint32_t)i < npx) v = gather_fetch(raw, W, H, opA, opB, flip ? W - 1 - x : x, y);
+                if (FULL || p + 32u * (uint32_t)i < npx) v = gather_fetch(raw, W, H, mA, opB, flip ? W - 1 - x : x, y);
                 my[lane + 32u * (uint32_t)i] = v;
                 x += 32;
                 if (x >= W) { x -= W; ++y; }
@@ -221,7 +228,7 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
                 if (p < npx) {
                     const uint32_t r = dw.div(p);
                     const int x = (int)(p - r * (uint32_t)W);
-                    v = gather_fetch(raw, W, H, opA, opB, flip ? W - 1 - x : x, oy0 + (int)r);
+                    v = gather_fetch(raw, W, H, mA, opB, flip ? W - 1 - x : x, oy0 + (int)r);
                 }
                 my[lane + 32u * (uint32_t)i] = v;
             }

@@ -1155,8 +1155,8 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 
 __device__ __forceinline__ bool scalar_stats_program(const Prog& g) {
     const int k0 = g.op[0].kind, k1 = g.op[1].kind;
-    return (g.cls == C_LUT || g.cls == C_GEOM) && (k0 == K_AUTOCONTRAST || k0 == K_CONTRAST) &&
-           (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS || k1 == K_AFFINE || k1 == K_SHIFT);
+    return (g.cls == C_LUT || g.cls == C_GEOM || g.cls == C_MAT) && (k0 == K_AUTOCONTRAST || k0 == K_CONTRAST) &&
+           (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS || k1 == K_AFFINE || k1 == K_SHIFT || k1 == K_SHARPNESS);
 }
 
 // returns with ftab / st.lutc complete (barrier included); the caller must call cluster_wait() once more before
@@ -1418,6 +1418,44 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
             if (clip) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
             else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
         }
+    } else if (cls == C_MAT) {
+        // pointwise op0 (per-channel LUT - static or from statistics - or Color), then Sharpness: op0 is applied IN PLACE to
+        // the staged rows (the raw bytes are not needed again; halo rows included), then the byte-stream Sharpness runs
+        bool peers_pending = false;
+        const int k0 = st.prog.op[0].kind;
+        const uint8_t* lut0 = st.lut[0];
+        if (kind_uses_lut(k0)) {
+            if (scalar_stats_program(st.prog)) {
+                build_scalar_stats_table<TAB>(P, s_norm, st, c, y0, y1, cluster, ftab);     // (the float table is not used here)
+                peers_pending = P.bands > 1;
+                lut0 = st.lutc;
+            } else if (st.prog.stat_mask & 1u) {
+                prepare_image(P, c, y0, y1, st, cluster);                                   // histogram path -> st.lut[0]
+            } else {
+                make_lut((uint32_t)P.H * (uint32_t)P.W, st, 0, 0u);                          // static LUT
+            }
+        }
+        {
+            const int ra = max(oy0 - 1, 0), rb = min(oy1 + 1, P.H);
+            const uint32_t nq = (uint32_t)(rb - ra) * ((uint32_t)P.W >> 2);
+            uint32_t* rows = reinterpret_cast<uint32_t*>(s_dyn + ((uint32_t)ra * (uint32_t)P.W * 3u - s_lo));
+            const float alpha0 = bits_to_float(st.prog.op[0].a[0]);
+            const bool clip0 = st.prog.op[0].a[1] != 0;
+            for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
+                uint32_t q[4];
+                unpack12(rows[3u * i], rows[3u * i + 1u], rows[3u * i + 2u], q);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] = k0 == K_COLOR ? color_px(q[k], alpha0, clip0) : apply_lut(lut0, q[k]);
+                rows[3u * i] = q[0] | (q[1] << 24);
+                rows[3u * i + 1u] = (q[1] >> 8) | (q[2] << 16);
+                rows[3u * i + 2u] = (q[2] >> 16) | (q[3] << 8);
+            }
+            __syncthreads();
+        }
+        const float alpha = bits_to_float(st.prog.op[1].a[0]);
+        if (st.prog.op[1].a[1]) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        if (peers_pending) cluster_wait();
     } else {                                                     // C_LUT with statistics
         bool peers_pending = false;
         if (scalar_stats_program(st.prog)) {
@@ -1516,7 +1554,8 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     bool done = false;
     if constexpr (OUT != OUT_U8_HWC) {
         // lean octet paths (faa_fast.cuh) for the common geometry; everything else takes the generic evaluators
-        if ((cls == C_GEOM || cls == C_POINT || cls == C_GEOM2) && octet_geometry(P, t) && band_fully_staged(c, t, oy0, oy1)) {
+        // (C_GEOM2 only exists in launches whose geometry the lean gather handles: build_prog, allow bit 2)
+        if (cls == C_GEOM2 || ((cls == C_GEOM || cls == C_POINT) && octet_geometry(P, t) && band_fully_staged(c, t, oy0, oy1))) {
             const int k0 = s_prog.op[0].kind, k1 = s_prog.op[1].kind;
             if (cls == C_GEOM2) {
                 // two gathers: out(x) = raw(map0(map1(x))), zero wherever either map leaves the image
@@ -1565,7 +1604,6 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
         case C_PLAIN: final_rows_plain_lut<OUT, TAB, false, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
         case C_LUT:   final_rows_plain_lut<OUT, TAB, true, true>(P, s_norm, s_ftab, c, s_lutc, t, out_img, oy0, oy1); break;
         case C_POINT: final_rows<OUT, TAB, C_POINT>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
-        case C_GEOM2: final_rows<OUT, TAB, C_GENERIC>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
         default:      final_rows<OUT, TAB, C_GEOM, false>(P, s_norm, c, s_lutc, t, out_img, oy0, oy1); break;
         }
     }

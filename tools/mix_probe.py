@@ -16,7 +16,7 @@ outs = [f.empty_out(B) for _ in range(4)]
 for i in range(5): f(x[i % 4], outs[i % 4], i * B)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 300
+n = int(os.environ.get("MIX_N", "1000"))
 e0.record()
 for i in range(n): f(x[i % 4], outs[i % 4], i * B)
 e1.record(); torch.cuda.synchronize()
