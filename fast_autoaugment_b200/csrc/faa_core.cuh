@@ -560,7 +560,14 @@ FAA_HD bool prog_is_mid(const Prog& g, int allow) {
     if (g.cls == C_GEOM) return (allow & 4) && g.stat_mask == 1 && (k0 == K_AUTOCONTRAST || k0 == K_EQUALIZE || k0 == K_CONTRAST) &&
                                 (k1 == K_AFFINE || k1 == K_SHIFT);
     // per-channel LUT (static or from statistics) or Color, then Sharpness: op0 is applied in place to the staged band
-    if (g.cls == C_MAT) return g.cls2 == C_SHARP && k1 == K_SHARPNESS && (kind_uses_lut(k0) || k0 == K_COLOR);
+    // ... or any materialisable op0 (per-channel LUT, Color, Cutout: in place; a gather: into the band buffer), then
+    // Sharpness or a statistics LUT on the materialised band
+    if (g.cls == C_MAT) {
+        const bool op0 = kind_uses_lut(k0) || k0 == K_COLOR || k0 == K_CUTOUT || k0 == K_AFFINE || k0 == K_SHIFT;
+        const bool op1 = (k1 == K_SHARPNESS && g.cls2 == C_SHARP) ||
+                         ((k1 == K_AUTOCONTRAST || k1 == K_EQUALIZE || k1 == K_CONTRAST) && g.cls2 == C_LUT);
+        return op0 && op1;
+    }
     return g.cls == C_SHARP && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
 }
 

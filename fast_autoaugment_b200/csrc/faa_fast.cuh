@@ -263,6 +263,40 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
     }
 }
 
+// rows [ra, rb) of a gathered image, materialised as uint8 HWC at `dst` (shared memory, byte 0 = pixel (0, ra)):
+// the same two-phase tile walk as the final pass, the quads are packed back into 12 bytes
+__device__ __forceinline__ void gather_rows_to_band(const AugParams& P, const uint8_t* raw, const OpRec* opA, uint8_t* dst,
+                                                    int ra, int rb, uint32_t* tile) {
+    const int W = P.W, H = P.H;
+    const uint32_t npx = (uint32_t)(rb - ra) * (uint32_t)W;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t* my = tile + warp * 128u;
+    const MapRegs mA = map_regs(*opA);
+    FastDiv dw; dw.init((uint32_t)W, P.rcp_w);
+    for (uint32_t base = warp * 128u; base < npx; base += nwarp * 128u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t p = base + lane + 32u * (uint32_t)i;
+            uint32_t v = 0u;
+            if (p < npx) {
+                const uint32_t r = dw.div(p);
+                v = gather_fetch(raw, W, H, mA, nullptr, (int)(p - r * (uint32_t)W), ra + (int)r) & 0xFFFFFFu;
+            }
+            my[lane + 32u * (uint32_t)i] = v;
+        }
+        __syncwarp();
+        const uint32_t p0 = base + 4u * lane;
+        if (p0 < npx) {
+            const uint4 q = reinterpret_cast<const uint4*>(my)[lane];
+            uint32_t* w = reinterpret_cast<uint32_t*>(dst + 3u * p0);
+            w[0] = q.x | (q.y << 24);
+            w[1] = (q.y >> 8) | (q.z << 16);
+            w[2] = (q.z >> 16) | (q.w << 8);
+        }
+        __syncwarp();
+    }
+}
+
 template <int OUT, bool USE_TAB>
 __device__ __forceinline__ void final_rows_gather(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
                                                   const OpRec* opA, const OpRec* opB, int flip, void* out_img, int oy0, int oy1,

@@ -1419,42 +1419,80 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
             else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
         }
     } else if (cls == C_MAT) {
-        // pointwise op0 (per-channel LUT - static or from statistics - or Color), then Sharpness: op0 is applied IN PLACE to
-        // the staged rows (the raw bytes are not needed again; halo rows included), then the byte-stream Sharpness runs
+        // op0 is MATERIALISED in the band buffer - a per-channel LUT (static or from statistics), Color or Cutout in place
+        // (the raw bytes are not needed again; halo rows included), a gather straight from global memory - then op1
+        // (Sharpness, or a statistics LUT) runs on the band as a single-op program
         bool peers_pending = false;
-        const int k0 = st.prog.op[0].kind;
-        const uint8_t* lut0 = st.lut[0];
-        if (kind_uses_lut(k0)) {
-            if (scalar_stats_program(st.prog)) {
-                build_scalar_stats_table<TAB>(P, s_norm, st, c, y0, y1, cluster, ftab);     // (the float table is not used here)
-                peers_pending = P.bands > 1;
-                lut0 = st.lutc;
-            } else if (st.prog.stat_mask & 1u) {
-                prepare_image(P, c, y0, y1, st, cluster);                                   // histogram path -> st.lut[0]
-            } else {
-                make_lut((uint32_t)P.H * (uint32_t)P.W, st, 0, 0u);                          // static LUT
+        const int k0 = st.prog.op[0].kind, k1 = st.prog.op[1].kind;
+        const int ra = max(oy0 - 1, 0), rb = min(oy1 + 1, P.H);
+        uint8_t* rows_b = s_dyn + ((uint32_t)ra * (uint32_t)P.W * 3u - s_lo);
+        if (k0 == K_AFFINE || k0 == K_SHIFT) {
+            gather_rows_to_band(P, c.raw, &st.prog.op[0], rows_b, ra, rb, s_tile);
+        } else {
+            const uint8_t* lut0 = st.lut[0];
+            if (kind_uses_lut(k0)) {
+                if (scalar_stats_program(st.prog)) {
+                    build_scalar_stats_table<TAB>(P, s_norm, st, c, y0, y1, cluster, ftab);     // (the float table is not used here)
+                    peers_pending = P.bands > 1;
+                    lut0 = st.lutc;
+                } else if (st.prog.stat_mask & 1u) {
+                    // histogram path of slot 0 only (prepare_image would also try slot 1)
+                    const uint32_t n_pixels = (uint32_t)P.H * (uint32_t)P.W;
+                    zero_stats(st);
+                    accumulate_stats<0>(c, kind_needs_hist(k0), kind_needs_mean(k0), y0, y1, st.hist[0], &st.suml[0]);
+                    const uint32_t mean = exchange_stats(P.bands, n_pixels, kind_needs_hist(k0), kind_needs_mean(k0), st, 0, cluster);
+                    make_lut(n_pixels, st, 0, mean);
+                } else {
+                    make_lut((uint32_t)P.H * (uint32_t)P.W, st, 0, 0u);                          // static LUT
+                }
             }
-        }
-        {
-            const int ra = max(oy0 - 1, 0), rb = min(oy1 + 1, P.H);
-            const uint32_t nq = (uint32_t)(rb - ra) * ((uint32_t)P.W >> 2);
-            uint32_t* rows = reinterpret_cast<uint32_t*>(s_dyn + ((uint32_t)ra * (uint32_t)P.W * 3u - s_lo));
+            const uint32_t qpr = (uint32_t)P.W >> 2, nq = (uint32_t)(rb - ra) * qpr;
+            uint32_t* rows = reinterpret_cast<uint32_t*>(rows_b);
             const float alpha0 = bits_to_float(st.prog.op[0].a[0]);
             const bool clip0 = st.prog.op[0].a[1] != 0;
+            const Box bx = st.prog.box[0];
+            FastDiv dq; dq.init(qpr, P.rcp_wq);
             for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
                 uint32_t q[4];
                 unpack12(rows[3u * i], rows[3u * i + 1u], rows[3u * i + 2u], q);
+                if (k0 == K_CUTOUT) {
+                    const uint32_t r = dq.div(i);
+                    const int y = ra + (int)r, x0 = (int)(i - r * qpr) * 4;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) q[k] = k0 == K_COLOR ? color_px(q[k], alpha0, clip0) : apply_lut(lut0, q[k]);
+                    for (int k = 0; k < 4; ++k)
+                        if (y >= bx.y0 && y <= bx.y1 && x0 + k >= bx.x0 && x0 + k <= bx.x1) q[k] = kCutoutRGB;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) q[k] = k0 == K_COLOR ? color_px(q[k], alpha0, clip0) : apply_lut(lut0, q[k]);
+                }
                 rows[3u * i] = q[0] | (q[1] << 24);
                 rows[3u * i + 1u] = (q[1] >> 8) | (q[2] << 16);
                 rows[3u * i + 2u] = (q[2] >> 16) | (q[3] << 8);
             }
-            __syncthreads();
         }
-        const float alpha = bits_to_float(st.prog.op[1].a[0]);
-        if (st.prog.op[1].a[1]) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
-        else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        __syncthreads();
+        if (k1 == K_SHARPNESS) {
+            const float alpha = bits_to_float(st.prog.op[1].a[0]);
+            if (st.prog.op[1].a[1]) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+            else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        } else {
+            // a statistics LUT on the materialised band: the program continues as the single-op program of slot 1
+            if (peers_pending) { cluster_wait(); peers_pending = false; }      // the record of slot 0's exchange is free again
+            if (threadIdx.x == 0) {
+                st.prog.op[0] = st.prog.op[1]; st.prog.op[1].kind = K_NONE;
+                st.prog.stat_mask = 1; st.prog.lut_mask = 1; st.prog.cls = C_LUT;
+            }
+            __syncthreads();
+            if (scalar_stats_program(st.prog)) {
+                build_scalar_stats_table<TAB>(P, s_norm, st, c, y0, y1, cluster, ftab);
+                peers_pending = P.bands > 1;
+            } else {
+                prepare_image(P, c, y0, y1, st, cluster);
+                build_ftab<TAB>(P, s_norm, st.lutc, ftab);
+            }
+            const float pad[3] = {0.0f, 0.0f, 0.0f};
+            final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
+        }
         if (peers_pending) cluster_wait();
     } else {                                                     // C_LUT with statistics
         bool peers_pending = false;
