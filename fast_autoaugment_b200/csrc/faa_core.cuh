@@ -553,22 +553,32 @@ FAA_HD bool prog_is_light(const Prog& g) {
 // "Mid" programs: whole-image statistics feeding per-channel LUTs, or Sharpness (+ a static LUT) - they need a
 // cluster (statistics exchange) or only halo rows, but none of the cluster kernel's materialisation / generic
 // machinery: they run in their own lean kernel when the launch geometry allows it (three-way split).
+// Two-stage programs of the mid kernel: stage A materialises op0 in the band buffer (per-channel LUT / Color / Cutout in
+// place, a gather from global memory, Sharpness through the global scratch image), stage B runs op1 on the band.
+FAA_HD bool prog_two_stage(const Prog& g, int allow) {
+    const int k0 = g.op[0].kind, k1 = g.op[1].kind;
+    const bool scratch = (allow & 2) != 0;
+    if (g.cls == C_MAT) {
+        const bool op0 = kind_uses_lut(k0) || k0 == K_COLOR || k0 == K_CUTOUT || k0 == K_AFFINE || k0 == K_SHIFT ||
+                         (k0 == K_SHARPNESS && scratch);
+        const bool op1 = (k1 == K_SHARPNESS && g.cls2 == C_SHARP) ||
+                         ((k1 == K_AUTOCONTRAST || k1 == K_EQUALIZE || k1 == K_CONTRAST) && g.cls2 == C_LUT);
+        return op0 && op1;
+    }
+    if (g.cls == C_SG) return true;                                                   // Sharpness, then a gather (scratch exists)
+    if (g.cls == C_SHARP) return scratch && (k1 == K_COLOR || k1 == K_CUTOUT);        // Sharpness, then Color / Cutout
+    if (g.cls == C_POINT) return g.stat_mask == 1 && (k1 == K_COLOR || k1 == K_CUTOUT);   // statistics LUT, then Color / Cutout
+    return false;
+}
+
 FAA_HD bool prog_is_mid(const Prog& g, int allow) {
     const int k0 = g.op[0].kind, k1 = g.op[1].kind;
     if (g.cls == C_LUT) return g.stat_mask != 0;
     // statistics LUT, then a gather: the table rides through the lean gather paths (fill colour = plain zero)
     if (g.cls == C_GEOM) return (allow & 4) && g.stat_mask == 1 && (k0 == K_AUTOCONTRAST || k0 == K_EQUALIZE || k0 == K_CONTRAST) &&
                                 (k1 == K_AFFINE || k1 == K_SHIFT);
-    // per-channel LUT (static or from statistics) or Color, then Sharpness: op0 is applied in place to the staged band
-    // ... or any materialisable op0 (per-channel LUT, Color, Cutout: in place; a gather: into the band buffer), then
-    // Sharpness or a statistics LUT on the materialised band
-    if (g.cls == C_MAT) {
-        const bool op0 = kind_uses_lut(k0) || k0 == K_COLOR || k0 == K_CUTOUT || k0 == K_AFFINE || k0 == K_SHIFT;
-        const bool op1 = (k1 == K_SHARPNESS && g.cls2 == C_SHARP) ||
-                         ((k1 == K_AUTOCONTRAST || k1 == K_EQUALIZE || k1 == K_CONTRAST) && g.cls2 == C_LUT);
-        return op0 && op1;
-    }
-    return g.cls == C_SHARP && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS);
+    if (g.cls == C_SHARP && (k1 == K_NONE || k1 == K_LUT || k1 == K_BRIGHTNESS)) return true;
+    return prog_two_stage(g, allow);
 }
 
 // Rough relative cost of an image (per-pixel work units) - only used to schedule the

@@ -182,18 +182,19 @@ __device__ __forceinline__ bool map_xy(const MapRegs& m, int& x, int& y, int W, 
 
 // one source pixel (24 bits) of the gather, bit 24 set when it exists.  mA maps the output pixel into the image in
 // front of the last op; opB (shared memory, may be null: CTA-uniform) maps that position into the image in front of it.
+template <bool COH = false>   // COH: the source image was written by this kernel (scratch, behind a cluster barrier): loads bypass L1
 __device__ __forceinline__ uint32_t gather_fetch(const uint8_t* raw, int W, int H, const MapRegs& mA, const OpRec* opB, int x, int y) {
     bool ok = map_xy(mA, x, y, W, H);
     if (opB != nullptr) { const MapRegs mB = map_regs(*opB); const bool ok2 = map_xy(mB, x, y, W, H); ok = ok && ok2; }
     const uint32_t off = ok ? (uint32_t)(y * W + x) * 3u : 0u;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + (off & ~3u));
-    const uint32_t lo = __ldg(wp);
-    const uint32_t hi = (off & 2u) ? __ldg(wp + 1) : 0u;                 // bytes 2,3 of the word: the pixel spills into the next one
+    const uint32_t lo = COH ? __ldcg(wp) : __ldg(wp);
+    const uint32_t hi = (off & 2u) ? (COH ? __ldcg(wp + 1) : __ldg(wp + 1)) : 0u;     // bytes 2,3 of the word: the pixel spills into the next one
     const uint32_t px = __funnelshift_r(lo, hi, 8u * (off & 3u)) & 0xFFFFFFu;
     return ok ? (px | 0x01000000u) : 0u;
 }
 
-template <int OUT, bool USE_TAB, bool FULL>
+template <int OUT, bool USE_TAB, bool FULL, bool COH = false>
 __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
                                                     const OpRec* opA, const OpRec* opB, int flip, void* out_img, int oy0, int oy1,
                                                     uint32_t* tile) {
@@ -215,7 +216,7 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint32_t v = 0u;
-                if (FULL || p + 32u * (uint32_t)i < npx) v = gather_fetch(raw, W, H, mA, opB, flip ? W - 1 - x : x, y);
+                if (FULL || p + 32u * (uint32_t)i < npx) v = gather_fetch<COH>(raw, W, H, mA, opB, flip ? W - 1 - x : x, y);
                 my[lane + 32u * (uint32_t)i] = v;
                 x += 32;
                 if (x >= W) { x -= W; ++y; }
@@ -228,7 +229,7 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
                 if (p < npx) {
                     const uint32_t r = dw.div(p);
                     const int x = (int)(p - r * (uint32_t)W);
-                    v = gather_fetch(raw, W, H, mA, opB, flip ? W - 1 - x : x, oy0 + (int)r);
+                    v = gather_fetch<COH>(raw, W, H, mA, opB, flip ? W - 1 - x : x, oy0 + (int)r);
                 }
                 my[lane + 32u * (uint32_t)i] = v;
             }
@@ -304,6 +305,13 @@ __device__ __forceinline__ void final_rows_gather(const AugParams& P, const floa
     const uint32_t npx = (uint32_t)(oy1 - oy0) * (uint32_t)P.W;
     if ((npx & 127u) == 0u) final_rows_gather_t<OUT, USE_TAB, true>(P, tab, pad, c, opA, opB, flip, out_img, oy0, oy1, tile);
     else final_rows_gather_t<OUT, USE_TAB, false>(P, tab, pad, c, opA, opB, flip, out_img, oy0, oy1, tile);
+}
+
+// the gather reads an image this kernel wrote (c.raw = scratch): coherent loads
+template <int OUT, bool USE_TAB>
+__device__ __forceinline__ void final_rows_gather_coh(const AugParams& P, const float* tab, const float pad[3], const Ctx& c,
+                                                      const OpRec* opA, int flip, void* out_img, int oy0, int oy1, uint32_t* tile) {
+    final_rows_gather_t<OUT, USE_TAB, false, true>(P, tab, pad, c, opA, nullptr, flip, out_img, oy0, oy1, tile);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -431,6 +439,16 @@ __device__ __forceinline__ uint32_t pair_lo(uint32_t w) { return __byte_perm(w, 
 __device__ __forceinline__ uint32_t pair_hi(uint32_t w) { return __byte_perm(w, 0u, 0x4342); }   // (b2, b3)
 
 // zb[12]: kBias15 + byte of the quad in source order -> normalised plane quads (FLIP: mirrored)
+// zb[12] -> 12 bytes of a uint8 HWC image (scratch images of Sharpness-first programs)
+__device__ __forceinline__ void sharp_emit_u8(const float zb[12], uint32_t* w) {
+    uint32_t b[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) b[k] = __float_as_uint(zb[k]) & 255u;
+    w[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    w[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    w[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+}
+
 template <int OUT, bool USE_TAB, bool FLIP>
 __device__ __forceinline__ void sharp_emit(const AugParams& P, const float* tab, const float zb[12], typename OutElem<OUT>::T* o,
                                            uint32_t plane) {
@@ -452,9 +470,10 @@ __device__ __forceinline__ void sharp_emit(const AugParams& P, const float* tab,
     }
 }
 
+// u8_dst != nullptr: the result goes, un-normalised and un-mirrored, to a uint8 HWC image (row 0 = image row 0)
 template <int OUT, bool USE_TAB, bool CLIP>
 __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const float* tab, const Ctx& c, float alpha, int flip,
-                                                  void* out_img, int oy0, int oy1) {
+                                                  void* out_img, int oy0, int oy1, uint8_t* u8_dst = nullptr) {
     using T = typename OutElem<OUT>::T;
     const int W = P.W, H = P.H;
     const uint32_t qpr = (uint32_t)W >> 2;
@@ -509,7 +528,9 @@ __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const floa
                 const float2 fdeg = __fadd2_rz(u, kk);                                                  // kBias15 + floor(u)
                 const float2 fctr = make_float2(biased_byte(wb[k0 >> 2], k0 & 3), biased_byte(wb[k1 >> 2], k1 & 3));
                 const float2 d = __ffma2_rn(fdeg, make_float2(-1.0f, -1.0f), fctr);                    // (float)(px - deg), exact
-                const float2 tt = __fadd2_rn(__fadd2_rn(fdeg, nk), __fmul2_rn(make_float2(alpha, alpha), d));   // Blend.c, no contraction
+                // Blend.c: product and sum are rounded SEPARATELY.  The product stays scalar: __fmul_rn is never contracted,
+                // whereas ptxas fuses a packed mul.f32x2 + add.f32x2 pair into one FFMA2 (seen with alpha = 1.72: wrong bytes)
+                const float2 tt = __fadd2_rn(__fadd2_rn(fdeg, nk), make_float2(__fmul_rn(alpha, d.x), __fmul_rn(alpha, d.y)));
                 float2 z = __fadd2_rz(tt, kk);
                 if (CLIP) {
                     z.x = fminf(fmaxf(z.x, kBias15), kBias15 + 255.0f);
@@ -527,9 +548,13 @@ __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const floa
                 for (int k = 9; k < 12; ++k) zb[k] = biased_byte(wb[3], k - 8);
             }
         }
-        T* o = dst + 4u * q;
-        if (flip) sharp_emit<OUT, USE_TAB, true>(P, tab, zb, o, plane);
-        else sharp_emit<OUT, USE_TAB, false>(P, tab, zb, o, plane);
+        if (u8_dst != nullptr) {
+            sharp_emit_u8(zb, reinterpret_cast<uint32_t*>(u8_dst + (uint32_t)y * pitch + 12u * sqx));
+        } else {
+            T* o = dst + 4u * q;
+            if (flip) sharp_emit<OUT, USE_TAB, true>(P, tab, zb, o, plane);
+            else sharp_emit<OUT, USE_TAB, false>(P, tab, zb, o, plane);
+        }
         qx += dxq; r += dr;
         if (qx >= qpr) { qx -= qpr; ++r; }
     }

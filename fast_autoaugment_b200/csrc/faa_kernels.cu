@@ -1363,6 +1363,34 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     (void)any_stats;   // statistics exchanges end with their own cluster barrier (build_slot_lut)
 }
 
+// a pointwise op applied in place to rows [r0, r1) of a uint8 HWC band whose byte 0 is pixel (0, ra): per-channel LUT
+// (`lut`), Color (augmentations.py:102-104) or the Cutout box (augmentations.py:142-143).  No barrier inside.
+__device__ __forceinline__ void inplace_pointwise(const AugParams& P, uint8_t* band, int ra, int r0, int r1, int kind, const OpRec& op,
+                                                  const Box bx, const uint8_t* lut) {
+    const uint32_t qpr = (uint32_t)P.W >> 2, nq = (uint32_t)(r1 - r0) * qpr;
+    uint32_t* rows = reinterpret_cast<uint32_t*>(band + (uint32_t)(r0 - ra) * (uint32_t)P.W * 3u);
+    const float alpha = bits_to_float(op.a[0]);
+    const bool clip = op.a[1] != 0;
+    FastDiv dq; dq.init(qpr, P.rcp_wq);
+    for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
+        uint32_t q[4];
+        unpack12(rows[3u * i], rows[3u * i + 1u], rows[3u * i + 2u], q);
+        if (kind == K_CUTOUT) {
+            const uint32_t r = dq.div(i);
+            const int y = r0 + (int)r, x0 = (int)(i - r * qpr) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (y >= bx.y0 && y <= bx.y1 && x0 + k >= bx.x0 && x0 + k <= bx.x1) q[k] = kCutoutRGB;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = kind == K_COLOR ? color_px(q[k], alpha, clip) : apply_lut(lut, q[k]);
+        }
+        rows[3u * i] = q[0] | (q[1] << 24);
+        rows[3u * i + 1u] = (q[1] >> 8) | (q[2] << 16);
+        rows[3u * i + 2u] = (q[2] >> 16) | (q[3] << 8);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // launch 2b: the "mid" kernel of a three-way split: statistics -> per-channel LUT programs (AutoContrast, Equalize,
 // Contrast, with static LUT partners) and Sharpness (+ static LUT).  One cluster per image like the cluster kernel
@@ -1406,28 +1434,44 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
     const Ctx c = make_ctx(P, P.in + (size_t)src_image(P, idx) * img_bytes, s_dyn, s_lo, s_len, P.H, P.W, st, true);
     const TailInfo t = make_tail(P, st.prog);
     float* ftab = reinterpret_cast<float*>(&st.hist[0][0]);      // 768 floats; the slot-0 histogram is idle by then
-    if (cls == C_SHARP) {
-        const float alpha = bits_to_float(st.prog.op[0].a[0]);
-        const bool clip = st.prog.op[0].a[1] != 0;
-        if (st.prog.op[1].kind != K_NONE) {                      // static LUT partner: rides in the float table
-            make_lut((uint32_t)P.H * (uint32_t)P.W, st, 1, 0u);
-            build_ftab<TAB>(P, s_norm, st.lut[1], ftab);
-            if (clip) final_rows_sharp4<OUT, true, true>(P, ftab, c, alpha, t.flip, out_img, oy0, oy1);
-            else final_rows_sharp4<OUT, true, false>(P, ftab, c, alpha, t.flip, out_img, oy0, oy1);
-        } else {
-            if (clip) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
-            else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
-        }
-    } else if (cls == C_MAT) {
-        // op0 is MATERIALISED in the band buffer - a per-channel LUT (static or from statistics), Color or Cutout in place
-        // (the raw bytes are not needed again; halo rows included), a gather straight from global memory - then op1
-        // (Sharpness, or a statistics LUT) runs on the band as a single-op program
+    if (prog_two_stage(st.prog, P.scratch != nullptr ? 2 : 0)) {
+        // Stage A materialises op0 in the band buffer: a per-channel LUT (static or from statistics), Color or Cutout in
+        // place (the raw bytes are not needed again; halo rows included); a gather straight from global memory; Sharpness
+        // through the global scratch image (its neighbours' rows come back from there).  Stage B runs op1 on the band as a
+        // single-op program: Sharpness, a statistics LUT, Color / Cutout - or, for Sharpness -> gather, reads the scratch.
         bool peers_pending = false;
         const int k0 = st.prog.op[0].kind, k1 = st.prog.op[1].kind;
         const int ra = max(oy0 - 1, 0), rb = min(oy1 + 1, P.H);
-        uint8_t* rows_b = s_dyn + ((uint32_t)ra * (uint32_t)P.W * 3u - s_lo);
+        const uint32_t pitch = (uint32_t)P.W * 3u;
+        uint8_t* rows_b = s_dyn + ((uint32_t)ra * pitch - s_lo);
+        bool done = false;
         if (k0 == K_AFFINE || k0 == K_SHIFT) {
             gather_rows_to_band(P, c.raw, &st.prog.op[0], rows_b, ra, rb, s_tile);
+        } else if (k0 == K_SHARPNESS) {
+            uint8_t* scr = P.scratch + (size_t)idx * img_bytes;
+            const float alpha0 = bits_to_float(st.prog.op[0].a[0]);
+            if (st.prog.op[0].a[1]) final_rows_sharp4<OUT, false, true>(P, nullptr, c, alpha0, 0, nullptr, y0, y1, scr);
+            else final_rows_sharp4<OUT, false, false>(P, nullptr, c, alpha0, 0, nullptr, y0, y1, scr);
+            __threadfence();
+            if (P.bands > 1) cluster.sync(); else __syncthreads();        // every band of the sharpened image is in the scratch
+            if (k1 == K_AFFINE || k1 == K_SHIFT) {                        // Sharpness -> gather: straight from the scratch image
+                Ctx cs = c; cs.raw = scr;
+                const float pad[3] = {normalise<TAB>(P, s_norm, 0, 0u), normalise<TAB>(P, s_norm, 1, 0u), normalise<TAB>(P, s_norm, 2, 0u)};
+                final_rows_gather_coh<OUT, TAB>(P, s_norm, pad, cs, &st.prog.op[1], t.flip, out_img, oy0, oy1, s_tile);
+                done = true;
+            } else {                                                      // back into the band buffer, halo rows from the peers' bands
+                const uint32_t n16 = ((uint32_t)(rb - ra) * pitch) >> 4;  // rows are multiples of 8 bytes; the pair of rows is 16
+                const uint4* g = reinterpret_cast<const uint4*>(scr + (uint32_t)ra * pitch);
+                uint4* d = reinterpret_cast<uint4*>(rows_b);
+                if ((((uint32_t)ra * pitch) & 15u) == 0u && (((uint32_t)(rb - ra) * pitch) & 15u) == 0u && ((reinterpret_cast<uintptr_t>(rows_b)) & 15u) == 0u) {
+                    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldcg(g + i);
+                } else {
+                    const uint32_t n4 = ((uint32_t)(rb - ra) * pitch) >> 2;
+                    const uint32_t* g4 = reinterpret_cast<const uint32_t*>(scr + (uint32_t)ra * pitch);
+                    uint32_t* d4 = reinterpret_cast<uint32_t*>(rows_b);
+                    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldcg(g4 + i);
+                }
+            }
         } else {
             const uint8_t* lut0 = st.lut[0];
             if (kind_uses_lut(k0)) {
@@ -1446,35 +1490,19 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
                     make_lut((uint32_t)P.H * (uint32_t)P.W, st, 0, 0u);                          // static LUT
                 }
             }
-            const uint32_t qpr = (uint32_t)P.W >> 2, nq = (uint32_t)(rb - ra) * qpr;
-            uint32_t* rows = reinterpret_cast<uint32_t*>(rows_b);
-            const float alpha0 = bits_to_float(st.prog.op[0].a[0]);
-            const bool clip0 = st.prog.op[0].a[1] != 0;
-            const Box bx = st.prog.box[0];
-            FastDiv dq; dq.init(qpr, P.rcp_wq);
-            for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) {
-                uint32_t q[4];
-                unpack12(rows[3u * i], rows[3u * i + 1u], rows[3u * i + 2u], q);
-                if (k0 == K_CUTOUT) {
-                    const uint32_t r = dq.div(i);
-                    const int y = ra + (int)r, x0 = (int)(i - r * qpr) * 4;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (y >= bx.y0 && y <= bx.y1 && x0 + k >= bx.x0 && x0 + k <= bx.x1) q[k] = kCutoutRGB;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) q[k] = k0 == K_COLOR ? color_px(q[k], alpha0, clip0) : apply_lut(lut0, q[k]);
-                }
-                rows[3u * i] = q[0] | (q[1] << 24);
-                rows[3u * i + 1u] = (q[1] >> 8) | (q[2] << 16);
-                rows[3u * i + 2u] = (q[2] >> 16) | (q[3] << 8);
-            }
+            inplace_pointwise(P, rows_b, ra, ra, rb, k0, st.prog.op[0], st.prog.box[0], lut0);
         }
         __syncthreads();
-        if (k1 == K_SHARPNESS) {
+        if (done) {
+        } else if (k1 == K_SHARPNESS) {
             const float alpha = bits_to_float(st.prog.op[1].a[0]);
             if (st.prog.op[1].a[1]) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
             else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        } else if (k1 == K_COLOR || k1 == K_CUTOUT) {
+            inplace_pointwise(P, rows_b, ra, oy0, oy1, k1, st.prog.op[1], st.prog.box[1], nullptr);
+            __syncthreads();
+            const float pad[3] = {0.0f, 0.0f, 0.0f};
+            final_rows_stream<OUT, TAB>(P, s_norm, pad, c, t, out_img, oy0, oy1);
         } else {
             // a statistics LUT on the materialised band: the program continues as the single-op program of slot 1
             if (peers_pending) { cluster_wait(); peers_pending = false; }      // the record of slot 0's exchange is free again
@@ -1494,6 +1522,18 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
             final_rows_stream<OUT, true>(P, ftab, pad, c, t, out_img, oy0, oy1);
         }
         if (peers_pending) cluster_wait();
+    } else if (cls == C_SHARP) {
+        const float alpha = bits_to_float(st.prog.op[0].a[0]);
+        const bool clip = st.prog.op[0].a[1] != 0;
+        if (st.prog.op[1].kind != K_NONE) {                      // static LUT partner: rides in the float table
+            make_lut((uint32_t)P.H * (uint32_t)P.W, st, 1, 0u);
+            build_ftab<TAB>(P, s_norm, st.lut[1], ftab);
+            if (clip) final_rows_sharp4<OUT, true, true>(P, ftab, c, alpha, t.flip, out_img, oy0, oy1);
+            else final_rows_sharp4<OUT, true, false>(P, ftab, c, alpha, t.flip, out_img, oy0, oy1);
+        } else {
+            if (clip) final_rows_sharp4<OUT, TAB, true>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+            else final_rows_sharp4<OUT, TAB, false>(P, s_norm, c, alpha, t.flip, out_img, oy0, oy1);
+        }
     } else {                                                     // C_LUT with statistics
         bool peers_pending = false;
         if (scalar_stats_program(st.prog)) {

@@ -31,6 +31,10 @@ def _policies():
     levels = (0.0, 0.07, 0.31, 0.5, 0.75, 0.93, 1.0)
     pols = [[(name, 1.0, lv), (name, 0.0, lv)] for name in ALL_OPS for lv in levels]          # single ops
     pols += [[(name, 0.0, lv), (name, 1.0, lv)] for name in ALL_OPS for lv in (0.2, 0.8)]     # ... in slot 1
+    # the fp32 blends over a sweep of alphas (rounding of alpha * (px - deg) decides bytes: a fused multiply-add is wrong
+    # for some alphas, e.g. level 0.9 -> alpha 1.72)
+    pols += [[(name, 1.0, k / 40.0), (name, 0.0, 0.5)] for name in ("Sharpness", "Color", "Brightness", "Contrast") for k in range(41)]
+    pols += [[("Sharpness", 1.0, 0.9), (b, 1.0, 0.37)] for b in ALL_OPS] + [[(a, 1.0, 0.37), ("Sharpness", 1.0, 0.9)] for a in ALL_OPS]
     for g in GEO:                                                                              # gather + LUT partner, both orders
         for l in LUTS:
             pols.append([(g, 1.0, rng.random()), (l, 1.0, rng.random())])
