@@ -685,12 +685,12 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC &&
                            (size_t)batch * h * w >= split_min;
     R.split = use_split ? 1 : 0;
-    // Chained steps (FAA_CHAIN=1|2; off by default): resolve(N+1), cluster(N), mid(N), light(N) all on the
+    // Chained steps (default; FAA_CHAIN=0 selects the event schedule): resolve(N+1), [cluster(N),] mid(N), light(N) all on the
     // caller's stream with programmatic dependent launches, no events and no side streams.  Consecutive steps
     // overlap (the next step's CTAs fill the slots the previous step's tail frees); the only true dependency -
     // programs written by the resolve kernel - is a ticket word the pixel kernels poll.  FAA_CHAIN=0: the
     // two-stream schedule with events (light kernel on the caller's stream, cluster kernel on a priority stream).
-    int chain_mode = 0;                                   // measured (profiles/r02_schedules.txt): the event schedule co-runs the kernels better
+    int chain_mode = 1;                                   // measured (profiles/r02_schedules.txt): 62.4 us chained vs 65.6 us with events
     if (const char* e = getenv("FAA_CHAIN")) chain_mode = atoi(e);
     const bool use_chain = chain_mode != 0 && use_split && allow_ahead && rng && !d_samples && !d_partner &&
                            !(getenv("FAA_AHEAD") && getenv("FAA_AHEAD")[0] == '0');
