@@ -68,6 +68,7 @@ def _load():
                                         vp, vp, P(Rng), vp, f32, f32, vp]),
         "faa_augment_host": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), P(Rng), vp]),
         "faa_mixup": (C.c_int, [vp, vp, vp, C.c_int, i64, C.c_int, f32, f32, vp]),
+        "faa_mix_u8": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), f32, f32, vp]),
         "faa_launch_count": (u64, []),
     }
     for name, (res, args) in sig.items():

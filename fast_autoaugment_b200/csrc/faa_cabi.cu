@@ -735,6 +735,9 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const bool no_heavy = use_mid && (R.allow & 6) == 6 && P.mat_cap > 0 && !heavy_always;
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
+    // fused Mixup mixes the fp32 normalised values before the output rounding: the fma shortcut is only proven to round
+    // like the exact value for a DIRECT fp16 / bf16 store, so two-source launches always take the exact table
+    if (d_partner) use_tab = true;
     // resolve-ahead: did the previous call already resolve exactly this batch on the side stream?
     const bool spec_ok = allow_ahead && !ahead_off && rng && !d_samples && !d_partner;
     faa_policy::AheadKey key; memset(&key, 0, sizeof key);
@@ -944,6 +947,30 @@ int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int f
     std::lock_guard<std::mutex> call_lk(p->call_mu);
     return augment_common(p, d_in_all, n_all, first, d_out, batch, h, w, tail, d_samples_all, d_boxes_all, rng, 0,
                           d_partner, lam, one_minus_lam, 1, false, stream);
+}
+
+int faa_mix_u8(faa_policy_t* p, const uint8_t* d_a, const uint8_t* d_b, const int32_t* d_partner, const int16_t* d_zero_box_a,
+               const int16_t* d_zero_box_b, void* d_out, int batch, int h, int w, const faa_tail_t* tail, float lam,
+               float one_minus_lam, void* stream) {
+    if (!p || ((!d_a || !d_b || !d_partner || !d_out) && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
+    if (batch < 0) return fail(FAA_ERR_VALUE, "negative batch");
+    if (int e = check_shape(h, w)) return e;
+    if (int e = check_tail(tail)) return e;
+    if (tail->out_dtype == FAA_U8_HWC) return fail(FAA_ERR_UNSUPPORTED, "mixup needs a float output");
+    if (tail->out_h != h || tail->out_w != w) return fail(FAA_ERR_VALUE, "the augmented images already have the output size");
+    if ((w & 3) || ((uintptr_t)d_a & 3) || ((uintptr_t)d_b & 3) || ((uintptr_t)d_out & 15))
+        return fail(FAA_ERR_UNSUPPORTED, "faa_mix_u8 needs W % 4 == 0 and aligned buffers");
+    if (!(lam >= 0.0f && lam <= 1.0f)) return fail(FAA_ERR_MAGNITUDE, "lam must be in [0, 1]");   // aug_mixup.py:20
+    if (int e = ensure_device()) return e;
+    if (batch == 0) return FAA_OK;
+    if (int e = bind_device(p)) return e;
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    AugParams dummy; bool tab = false;
+    if (int e = normalisation(p, tail, dummy, tab, (cudaStream_t)stream)) return e;
+    CK(launch_mix_u8(d_a, d_b, d_partner, d_zero_box_a, d_zero_box_b, p->d_norm, d_out, batch, h, w, tail->out_dtype, lam,
+                     one_minus_lam, (cudaStream_t)stream));
+    g_launches++;
+    return FAA_OK;
 }
 
 int faa_mixup(const void* d_data, void* d_out, const int64_t* d_perm, int batch, int64_t n_per_sample, int dtype,

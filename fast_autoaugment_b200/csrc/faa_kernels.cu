@@ -1743,6 +1743,96 @@ __global__ void __launch_bounds__(256) faa_mixup_kernel_v(const T* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
+// Mixup of AUGMENTED uint8 images (aug_mixup.py:13-23 behind data.py's ToTensor + Normalize + CutoutDefault):
+//     out[i] = norm(a_i) * lam + norm(b_i) * (1 - lam)           (fp32, separate roundings, then the output dtype)
+// a = this sample's augmented uint8 HWC image, b = its partner's (same array or a received one); the CutoutDefault
+// boxes act on the normalised values, so each source brings its own zero box.  The op streams: 6 bytes in, 3 values
+// out per pixel; one quad per thread and iteration, 8-byte plane stores.
+struct MixU8Params {
+    const uint8_t* a;            // [batch][H][W][3]
+    const uint8_t* b;            // partner pool [nb][H][W][3]
+    const int32_t* partner;      // [batch] index into b
+    const int16_t* zb_a;         // [batch][4] zero boxes (y0, y1, x0, x1; half-open) or nullptr
+    const int16_t* zb_b;         // [nb][4] or nullptr
+    const float* norm_tab;       // [3][256] exact ToTensor+Normalize values
+    void* out;                   // [batch][3][H][W]
+    int32_t H, W;
+    float lam, oml;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) faa_mix_u8_kernel(const __grid_constant__ MixU8Params P) {
+    __shared__ float s_tab[768];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_tab[i] = __ldg(P.norm_tab + i);
+    __syncthreads();
+    const int img = blockIdx.y, pi = __ldg(P.partner + img);
+    const uint32_t npx = (uint32_t)P.H * (uint32_t)P.W, nq = npx >> 2;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(P.a + (size_t)img * npx * 3u);
+    const uint32_t* b = reinterpret_cast<const uint32_t*>(P.b + (size_t)pi * npx * 3u);
+    T* o = reinterpret_cast<T*>(P.out) + (size_t)img * npx * 3u;
+    int za[4] = {0, 0, 0, 0}, zb[4] = {0, 0, 0, 0};
+    if (P.zb_a) for (int k = 0; k < 4; ++k) za[k] = P.zb_a[img * 4 + k];
+    if (P.zb_b) for (int k = 0; k < 4; ++k) zb[k] = P.zb_b[pi * 4 + k];
+    const bool boxes = (za[1] > za[0] && za[3] > za[2]) || (zb[1] > zb[0] && zb[3] > zb[2]);
+    const uint32_t qpr = (uint32_t)P.W >> 2;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        uint32_t pa[4], pb[4];
+        unpack12(__ldg(a + 3u * q), __ldg(a + 3u * q + 1u), __ldg(a + 3u * q + 2u), pa);
+        unpack12(__ldg(b + 3u * q), __ldg(b + 3u * q + 1u), __ldg(b + 3u * q + 2u), pb);
+        uint32_t ma = 0u, mb = 0u;                           // pixels of the quad inside the zero boxes
+        if (boxes) {
+            const int y = (int)(q / qpr), x0 = (int)(q - (uint32_t)y * qpr) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ma |= (uint32_t)(y >= za[0] && y < za[1] && x0 + k >= za[2] && x0 + k < za[3]) << k;
+                mb |= (uint32_t)(y >= zb[0] && y < zb[1] && x0 + k >= zb[2] && x0 + k < zb[3]) << k;
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float fa = ((ma >> k) & 1u) ? 0.0f : s_tab[ch * 256 + ((pa[k] >> (8 * ch)) & 255u)];
+                const float fb = ((mb >> k) & 1u) ? 0.0f : s_tab[ch * 256 + ((pb[k] >> (8 * ch)) & 255u)];
+                v[k] = f_add(f_mul(fa, P.lam), f_mul(fb, P.oml));                 // aug_mixup.py:21
+            }
+            T* op = o + (size_t)ch * npx + 4u * q;
+            if constexpr (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+            } else if constexpr (std::is_same<T, __half>::value) {
+                __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(op) = u;
+            } else {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                uint2 u; u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(op) = u;
+            }
+        }
+    }
+}
+
+cudaError_t launch_mix_u8(const uint8_t* a, const uint8_t* b, const int32_t* partner, const int16_t* zb_a, const int16_t* zb_b,
+                          const float* norm_tab, void* out, int batch, int H, int W, int dtype, float lam, float oml,
+                          cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    MixU8Params P; P.a = a; P.b = b; P.partner = partner; P.zb_a = zb_a; P.zb_b = zb_b; P.norm_tab = norm_tab; P.out = out;
+    P.H = H; P.W = W; P.lam = lam; P.oml = oml;
+    const uint32_t nq = (uint32_t)H * (uint32_t)W / 4u;
+    unsigned gx = (nq + 255u) / 256u;
+    if (gx > 8) gx = 8;                                      // ~6 quads per thread at 224x224
+    dim3 grid(gx, (unsigned)batch, 1);
+    switch (dtype) {
+    case OUT_F16:  faa_mix_u8_kernel<__half><<<grid, 256, 0, stream>>>(P); break;
+    case OUT_BF16: faa_mix_u8_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(P); break;
+    case OUT_F32:  faa_mix_u8_kernel<float><<<grid, 256, 0, stream>>>(P); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 int pick_bands(int H, int W, int out_h, int out_w) {
     // aim for >= ~1024 output quads per CTA; cluster size must be a power of two <= 8
     long long quads = (long long)out_h * ((out_w + 3) / 4);

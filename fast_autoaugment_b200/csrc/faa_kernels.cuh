@@ -77,6 +77,10 @@ cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, int w
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,
                          int dtype, float lam, float one_minus_lam, cudaStream_t stream);
 
+cudaError_t launch_mix_u8(const uint8_t* a, const uint8_t* b, const int32_t* partner, const int16_t* zb_a, const int16_t* zb_b,
+                          const float* norm_tab, void* out, int batch, int H, int W, int dtype, float lam, float one_minus_lam,
+                          cudaStream_t stream);
+
 int pick_bands(int H, int W, int out_h, int out_w);
 void fill_geom(BandGeom& g, int bands, int H, int W, int out_h, int crop_pad, bool stage);
 uint32_t band_capacity(int bands, int H, int W, int out_h, int crop_pad);

@@ -123,12 +123,37 @@ def philox_records(policy: CompiledPolicy, n: int, h: int, w: int, tail: TailSpe
     return d_s, d_b
 
 
+def mix_augmented(policy: CompiledPolicy, a_u8: torch.Tensor, pool_u8: torch.Tensor, partner_pool: torch.Tensor, tail: TailSpec,
+                  lam: float, zero_box_a=None, zero_box_pool=None, out=None):
+    """``norm(a[i]) * lam + norm(pool[partner_pool[i]]) * (1 - lam)`` for AUGMENTED uint8 HWC images (C ABI ``faa_mix_u8``):
+    ToTensor + Normalize + CutoutDefault boxes (int16 [n,4] CUDA tensors, half-open y0,y1,x0,x1) + aug_mixup.py:21."""
+    b, h, w, _ = a_u8.shape
+    t = tail.c_struct(h, w)
+    if out is None:
+        out = torch.empty((b, 3, h, w), dtype=tail.out_dtype, device=a_u8.device)
+    part = partner_pool.to(device=a_u8.device, dtype=torch.int32).contiguous()
+    za = zero_box_a.contiguous() if zero_box_a is not None else None
+    zp = zero_box_pool.contiguous() if zero_box_pool is not None else None
+    with torch.cuda.device(a_u8.device):
+        _lib.check(_lib.lib.faa_mix_u8(policy.handle, a_u8.data_ptr(), pool_u8.data_ptr(), part.data_ptr(),
+                                       za.data_ptr() if za is not None else None, zp.data_ptr() if zp is not None else None,
+                                       out.data_ptr(), b, h, w, C.byref(t), float(np.float32(lam)), float(np.float32(1 - lam)),
+                                       C.c_void_p(torch.cuda.current_stream(a_u8.device).cuda_stream)))
+    return out
+
+
 def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
                  seed: int, step: int, group=None, timing=None):
-    """Augment this rank's shard and mix every sample with its partner from the GLOBAL batch; partners travel
-    by a partner-only all-to-all of raw uint8 images (module doc).  Returns ``(data, targets, partner_targets,
-    lam)`` like reference ``mixup`` (aug_mixup.py:23).  ``timing``: optional dict, receives CUDA events
-    ``ex0``/``ex1`` around the exchange and ``recv_bytes``."""
+    """Augment this rank's shard and mix every sample with its partner from the GLOBAL batch (module doc):
+
+    1. the shard is augmented ONCE, to uint8 HWC (policy + RandomCrop + HFlip; decisions = Philox keyed by the global
+       sample index);
+    2. partner-only all-to-all of the AUGMENTED uint8 images (3 B/px; a rank receives only what its samples pair with);
+    3. one streaming pass (``faa_mix_u8``) normalises both sources, applies each source's CutoutDefault box and mixes in fp32.
+
+    Returns ``(data, targets, partner_targets, lam)`` like reference ``mixup`` (aug_mixup.py:23); the values equal the
+    fused single-GPU launch ``augment_batch(..., partner=perm, lam=lam)`` on the global batch.  ``timing``: optional dict,
+    receives CUDA events ``ex0``/``ex1`` around the exchange and ``recv_bytes``."""
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
     b, h, w = local_u8.shape[0], local_u8.shape[1], local_u8.shape[2]
     n = b * world
@@ -136,20 +161,33 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
     perm, lam = global_pairing(n, alpha, seed, step)
     lo, _ = shard_bounds(n, rank, world)
     send_idx, send_counts, recv_counts, partner_pool, recv_global = partner_plan(perm, rank, world)
+    # 1. this shard, augmented to uint8 (the CutoutDefault box acts on the normalised tensor: step 3)
+    u8_tail = TailSpec(tail.out_size, tail.crop_pad, tail.hflip, tail.mean, tail.std, 0, torch.uint8)
+    rng = make_rng(seed, step * n + lo, tail)
+    rng.zero_box_len = 0                                         # (its Philox block is separate: the other draws do not move)
+    oh, ow = tail.out_size if tail.out_size is not None else (h, w)
+    n_recv = sum(recv_counts)
+    pool = torch.empty((b + n_recv, oh, ow, 3), dtype=torch.uint8, device=dev)      # [own augmented shard | received partners]
+    aug = augment_batch(policy, local_u8, u8_tail, rng=rng, out=pool[:b])
+    # 2. partners: straight into the tail of the pool
     if timing is not None:
         timing["ex0"] = torch.cuda.Event(enable_timing=True); timing["ex0"].record()
-    recv = exchange_partners(local_u8, send_idx, send_counts, recv_counts, group) if world > 1 else local_u8[:0]
+    if world > 1:
+        send = aug.index_select(0, send_idx.to(dev))
+        dist.all_to_all_single(pool[b:], send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=group)
     all_targets = gather_pool(targets, group) if world > 1 else targets
     if timing is not None:
         timing["ex1"] = torch.cuda.Event(enable_timing=True); timing["ex1"].record()
-        timing["recv_bytes"] = int(recv.numel())
-    pool = torch.cat([local_u8, recv]) if recv.shape[0] else local_u8
-    # decisions: the device sampler's records of the global batch, in pool order
-    rec_s, rec_b = philox_records(policy, n, h, w, tail, seed, step * n, dev)
-    ids = torch.cat([torch.arange(lo, lo + b, dtype=torch.int64), recv_global]).to(dev)
-    pool_s, pool_b = rec_s.index_select(0, ids).reshape(-1), rec_b.index_select(0, ids).reshape(-1)
-    data = augment_batch(policy, local_u8, tail, partner=partner_pool, lam=lam, pool=pool, pool_samples=pool_s,
-                         pool_boxes=pool_b, first=0)
+        timing["recv_bytes"] = int(n_recv) * oh * ow * 3
+    # 3. zero boxes of every source (decisions are a function of the global index: no communication), then the mix
+    za = zp = None
+    if tail.cutout > 0:
+        rec_s, _ = philox_records(policy, n, h, w, tail, seed, step * n, dev)
+        zb_all = rec_s[:, 8:16].contiguous().view(torch.int16)                      # faa_sample_t.zero_box
+        ids = torch.cat([torch.arange(lo, lo + b, dtype=torch.int64), recv_global]).to(dev)
+        zp = zb_all.index_select(0, ids)
+        za = zp[:b]
+    data = mix_augmented(policy, aug, pool, partner_pool, tail, lam, za, zp)
     return data, targets, all_targets[perm[lo:lo + b].to(all_targets.device)], lam
 
 

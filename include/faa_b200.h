@@ -182,6 +182,17 @@ int faa_augment_host(faa_policy_t* p, const uint8_t* h_in, void* h_out, void* d_
 int faa_mixup(const void* d_data, void* d_out, const int64_t* d_perm, int batch,
               int64_t n_per_sample, int dtype, float lam, float one_minus_lam, void* stream);
 
+/* ---- Mixup of AUGMENTED uint8 images (the multi-GPU / large-batch route): the policy part of the
+ * chain ran with a uint8 HWC output (faa_augment with tail.out_dtype = FAA_U8_HWC: policy + crop +
+ * flip), possibly on another GPU; this call finishes data.py:42-43 (ToTensor, Normalize), data.py:228-250
+ * (CutoutDefault: one half-open zero box [y0,y1)x[x0,x1) per SOURCE image, int16[4] each, may be NULL) and
+ * aug_mixup.py:21 in one streaming pass:
+ *     d_out[i] = norm(d_a[i]) * lam + norm(d_b[d_partner[i]]) * one_minus_lam      (fp32, then tail->out_dtype)
+ * Same values as faa_augment_mixup on the raw images.  W % 4 == 0. */
+int faa_mix_u8(faa_policy_t* p, const uint8_t* d_a, const uint8_t* d_b, const int32_t* d_partner,
+               const int16_t* d_zero_box_a, const int16_t* d_zero_box_b, void* d_out, int batch, int h, int w,
+               const faa_tail_t* tail, float lam, float one_minus_lam, void* stream);
+
 /* number of kernels this library has launched since load (bench bookkeeping) */
 uint64_t faa_launch_count(void);
 

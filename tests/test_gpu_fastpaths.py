@@ -117,3 +117,28 @@ def test_tta_replicas_equal_single_launches(B, shape, replicas, dtype, cutout, s
         want = augment_batch(ref_pol, x, tail, rng=make_rng(9, 1000 + r * B, tail))
         assert torch.equal(got[r], want), r
     assert not torch.equal(got[0], got[1])
+
+
+@pytest.mark.parametrize("shape,kind,dtype", [((32, 32), "cifar", torch.float32), ((224, 224), "imagenet", torch.float16),
+                                              ((56, 104), "imagenet_cutout", torch.float32)])
+def test_mixup_of_augmented_u8_equals_the_fused_launch(shape, kind, dtype):
+    """BASELINE config 4 route (augment once to uint8, exchange, faa_mix_u8) == the fused two-source launch == the
+    reference formula data*lam + data[perm]*(1-lam) on the normalised fp32 tensors (aug_mixup.py:21)"""
+    from fast_autoaugment_b200 import archive
+    from fast_autoaugment_b200.distributed import global_pairing, mixup_global
+    from fast_autoaugment_b200.engine import make_rng
+    H, W = shape
+    n = 96
+    pol = CompiledPolicy(archive.fa_reduced_cifar10() if kind == "cifar" else archive.fa_resnet50_rimagenet())
+    tail = TailSpec.cifar(16, dtype) if kind == "cifar" else TailSpec.imagenet(16 if kind.endswith("cutout") else 0, dtype)
+    x = torch.from_numpy(synth_batch(n, shape, seed=12)).cuda()
+    y = torch.arange(n).cuda()
+    data, t1, t2, lam = mixup_global(pol, x, y, tail, 0.2, seed=3, step=2)
+    perm, lam2 = global_pairing(n, 0.2, seed=3, step=2)
+    assert lam == lam2 and torch.equal(t2.cpu(), perm) and torch.equal(t1, y)
+    fused = augment_batch(CompiledPolicy(pol.policies), x, tail, rng=make_rng(3, 2 * n, tail), partner=perm, lam=lam)
+    assert torch.equal(data, fused)
+    if dtype == torch.float32:
+        plain = augment_batch(CompiledPolicy(pol.policies), x, tail, rng=make_rng(3, 2 * n, tail))
+        ref = plain * np.float32(lam) + plain[perm.cuda()] * np.float32(1 - lam)
+        assert torch.equal(data, ref)
