@@ -15,7 +15,8 @@ from . import _lib                      # noqa: F401  (fails loudly if the CUDA 
 from . import archive                   # noqa: F401
 from .engine import (CompiledPolicy, FusedAugmenter, TailSpec, augment_batch, augment_tta, make_rng,   # noqa: F401
                      CIFAR_MEAN, CIFAR_STD, IMAGENET_MEAN, IMAGENET_STD)
-from .data import Augmentation, CutoutDefault, GpuAugmentedLoader, get_dataloaders   # noqa: F401
+from .data import (Augmentation, ColorJitter, CutoutDefault, GpuAugmentedLoader, Lighting,   # noqa: F401
+                   get_dataloaders)
 from .aug_mixup import mixup                                                      # noqa: F401
 
 __version__ = "0.1.0"

@@ -24,6 +24,7 @@ SAMPLE_DTYPE = np.dtype([("sub", "<u2"), ("gate", "u1"), ("sign", "u1"), ("crop_
                          ("crop_dx", "i1"), ("flip", "u1"), ("reserved", "u1"),
                          ("zero_box", "<i2", (4,))])
 BOX_DTYPE = np.dtype([("x0", "<i2"), ("y0", "<i2"), ("x1", "<i2"), ("y1", "<i2")])
+JITTER_DTYPE = np.dtype([("alpha", "<f4", (3,)), ("order", "u1", (4,))])          # faa_jitter_t
 assert SAMPLE_DTYPE.itemsize == 16 and BOX_DTYPE.itemsize == 8
 
 
@@ -69,6 +70,8 @@ def _load():
         "faa_augment_host": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), P(Rng), vp]),
         "faa_mixup": (C.c_int, [vp, vp, vp, C.c_int, i64, C.c_int, f32, f32, vp]),
         "faa_mix_u8": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), f32, f32, vp]),
+        "faa_color_jitter": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "faa_policy_set_lighting": (C.c_int, [vp, vp, C.c_int]),
         "faa_launch_count": (u64, []),
     }
     for name, (res, args) in sig.items():

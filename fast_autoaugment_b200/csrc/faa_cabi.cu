@@ -222,6 +222,8 @@ struct faa_policy {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     cudaEvent_t ev_host_done = nullptr; bool host_in_flight = false;   // faa_augment_host: last call's work (it owns d_in / stages)
     std::mutex call_mu;                  // launches of one policy are serialised (speculation state, slots, staging)
+    const float* lighting_rgb = nullptr; int lighting_n = 0;       // Lighting offsets [n][3] (device) for the next launches, or null
+    float* d_norm_img = nullptr; size_t d_norm_img_bytes = 0;      // per-image normalisation tables [n][3][256]
     int device = -1;                     // the device that owns every buffer / stream / event above (-1: none yet)
     int32_t ticket = 0;                  // chained steps: id of the last resolve launch
     int32_t ahead_ticket = 0;
@@ -318,6 +320,7 @@ int faa_policy_destroy(faa_policy_t* p) {
     if (p->d_progs) cudaFree(p->d_progs);
     if (p->d_order) cudaFree(p->d_order);
     if (p->d_scratch) cudaFree(p->d_scratch);
+    if (p->d_norm_img) cudaFree(p->d_norm_img);
     if (p->d_in) cudaFree(p->d_in);
     if (p->d_out) cudaFree(p->d_out);
     if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
@@ -735,6 +738,21 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const bool no_heavy = use_mid && (R.allow & 6) == 6 && P.mat_cap > 0 && !heavy_always;
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
+    if (p->lighting_rgb && tail->out_dtype != FAA_U8_HWC && apply_tail) {
+        // Lighting (augmentations.py:197-215): one normalisation table per image, built on the stream in torch's fp32 order
+        if (d_partner) return fail(FAA_ERR_UNSUPPORTED, "Lighting together with fused Mixup is not supported");
+        if (p->lighting_n != n_all) return fail(FAA_ERR_VALUE, "faa_policy_set_lighting was given a different number of images");
+        const size_t need = (size_t)n_all * 768 * sizeof(float);
+        if (p->d_norm_img_bytes < need) {
+            if (p->d_norm_img) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(p->d_norm_img)); p->d_norm_img = nullptr; p->d_norm_img_bytes = 0; }
+            CK(cudaMalloc(&p->d_norm_img, need));
+            p->d_norm_img_bytes = need;
+        }
+        CK(launch_lighting_tables(p->lighting_rgb, p->d_norm_img, n_all, tail->mean, tail->std, stream));
+        g_launches++;
+        P.norm_tab = p->d_norm_img; P.norm_stride = 768;
+        use_tab = true;
+    }
     // fused Mixup mixes the fp32 normalised values before the output rounding: the fma shortcut is only proven to round
     // like the exact value for a DIRECT fp16 / bf16 store, so two-source launches always take the exact table
     if (d_partner) use_tab = true;
@@ -744,7 +762,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     if (spec_ok) {
         key.seed = rng->seed; key.first_index = rng->first_index;
         const int32_t v[16] = {batch, n_all, first, h, w, tail->out_h, tail->out_w, op_base, apply_tail, R.allow, R.split,
-                               rng->crop_pad, rng->hflip, rng->zero_box_len, (use_order ? 1 : 0) | (in_mod << 1), use_chain ? 1 : 0};
+                               rng->crop_pad, rng->hflip, rng->zero_box_len, (use_order ? 1 : 0) | (in_mod << 1), (use_chain ? 1 : 0) | (P.norm_stride ? 2 : 0)};
         memcpy(key.v, v, sizeof v);
     }
     auto set_mid_geometry = [&](AugParams& a) {
@@ -947,6 +965,25 @@ int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int f
     std::lock_guard<std::mutex> call_lk(p->call_mu);
     return augment_common(p, d_in_all, n_all, first, d_out, batch, h, w, tail, d_samples_all, d_boxes_all, rng, 0,
                           d_partner, lam, one_minus_lam, 1, false, stream);
+}
+
+int faa_policy_set_lighting(faa_policy_t* p, const float* d_rgb, int n) {
+    if (!p) return fail(FAA_ERR_VALUE, "null policy");
+    if (d_rgb && n <= 0) return fail(FAA_ERR_VALUE, "n must be positive");
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    p->lighting_rgb = d_rgb; p->lighting_n = d_rgb ? n : 0;
+    return FAA_OK;
+}
+
+int faa_color_jitter(const uint8_t* d_in, uint8_t* d_out, int batch, int h, int w, const faa_jitter_t* d_recs, void* stream) {
+    if ((!d_in || !d_out || !d_recs) && batch > 0) return fail(FAA_ERR_VALUE, "null argument");
+    if (batch < 0) return fail(FAA_ERR_VALUE, "negative batch");
+    if (int e = check_shape(h, w)) return e;
+    if (int e = ensure_device()) return e;
+    static_assert(sizeof(faa_jitter_t) == 16, "jitter record is 16 bytes");
+    CK(launch_color_jitter(d_in, d_out, d_recs, batch, h, w, (cudaStream_t)stream));
+    if (batch > 0) g_launches++;
+    return FAA_OK;
 }
 
 int faa_mix_u8(faa_policy_t* p, const uint8_t* d_a, const uint8_t* d_b, const int32_t* d_partner, const int16_t* d_zero_box_a,

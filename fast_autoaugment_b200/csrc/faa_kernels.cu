@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
     const uint32_t s_lo = P.geo[0].lo[band], s_len = P.geo[0].len[band];
-    if (TAB)
+    if (TAB && !P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
 
     // Programmatic dependent launch: everything above overlaps the resolve kernel's tail; the
@@ -1293,6 +1293,8 @@ __global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_
     int src_idx[NSRC];
     src_idx[0] = P.first + img;
     if constexpr (NSRC == 2) src_idx[1] = P.partner[img];
+    if (TAB && P.norm_stride)                                   // Lighting: this image's own normalisation table
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + (size_t)src_idx[0] * P.norm_stride + i);
 
     // 0. stage the raw row band(s): one TMA bulk copy each, in flight while the program loads
     if (threadIdx.x == 0 && s_len) {
@@ -1412,13 +1414,15 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
     const uint32_t s_lo = P.geo[0].lo[band], s_len = P.geo[0].len[band];
-    if (TAB)
+    if (TAB && !P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
     const int e0 = ld_sched(P.n_heavy, P.chain), e1 = ld_sched(P.n_heavy + 1, P.chain);
     if ((int)blockIdx.y >= e1 - e0) return;                      // cluster-uniform
     const int img = ld_sched(P.order + P.first + e0 + blockIdx.y, P.chain);
     const int idx = P.first + img;
+    if (TAB && P.norm_stride)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + (size_t)idx * P.norm_stride + i);
     if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)src_image(P, idx) * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
         reinterpret_cast<uint32_t*>(&st.prog)[threadIdx.x] = ld_sched(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x, P.chain);
@@ -1584,13 +1588,15 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     const int band = blockIdx.x;
     const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
     const uint32_t s_lo = P.geo[1].lo[band], s_len = P.geo[1].len[band];
-    if (TAB)
+    if (TAB && !P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
     const int n_heavy = ld_sched(P.n_heavy + 1, P.chain);       // entries in front of the light segment (heavy + mid)
     if ((int)blockIdx.y >= P.B - n_heavy) return;
     const int img = ld_sched(P.order + P.first + n_heavy + blockIdx.y, P.chain);     // uniform load per warp
     const int idx = P.first + img;
+    if (TAB && P.norm_stride)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + (size_t)idx * P.norm_stride + i);
     if (threadIdx.x == 0 && s_len) tma_stage(&s_bar, s_dyn, P.in + (size_t)src_image(P, idx) * img_bytes + s_lo, s_len);
     if (threadIdx.x < sizeof(Prog) / 4)
         reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = ld_sched(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x, P.chain);
@@ -1740,6 +1746,85 @@ __global__ void __launch_bounds__(256) faa_mixup_kernel_v(const T* __restrict__ 
         }
         o[i] = r;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// torchvision ColorJitter(brightness, contrast, saturation) of the ImageNet train chain (data.py:65-69) on uint8 HWC
+// images: per image a random order of up to three ImageEnhance blends with per-image factors - Brightness (with
+// black), Contrast (with the rounded mean luma of the CURRENT image), Color (with the pixel's luma) - i.e. the
+// arithmetic of the policy ops K_BRIGHTNESS / K_CONTRAST / K_COLOR (faa_core.cuh) with magnitudes that are not
+// policy constants.  One CTA per image; every op is one pass over the image in place (Contrast: a reduction first).
+struct JitterRec { float alpha[3]; uint8_t order[4]; };     // == faa_jitter_t; order[]: torch.randperm(4), id 3 = hue (absent)
+
+__global__ void __launch_bounds__(1024) faa_color_jitter_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                                const JitterRec* __restrict__ recs, int H, int W) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ unsigned long long s_sum;
+    const int img = blockIdx.x;
+    const uint32_t npx = (uint32_t)H * (uint32_t)W;
+    const uint8_t* src = in + (size_t)img * npx * 3u;
+    uint8_t* dst = out + (size_t)img * npx * 3u;
+    const JitterRec r = recs[img];
+    bool first = true;
+    for (int step = 0; step < 4; ++step) {
+        const int id = r.order[step];
+        if (id > 2) continue;
+        const float alpha = r.alpha[id];
+        const bool clip = !(alpha >= 0.0f && alpha <= 1.0f);
+        const uint8_t* cur = first ? src : dst;
+        if (id == 2) {                                       // saturation: ImageEnhance.Color
+            for (uint32_t i = threadIdx.x; i < npx; i += blockDim.x) {
+                const uint32_t p = (uint32_t)cur[3u * i] | ((uint32_t)cur[3u * i + 1u] << 8) | ((uint32_t)cur[3u * i + 2u] << 16);
+                const uint32_t q = color_px(p, alpha, clip);
+                dst[3u * i] = (uint8_t)q; dst[3u * i + 1u] = (uint8_t)(q >> 8); dst[3u * i + 2u] = (uint8_t)(q >> 16);
+            }
+        } else {
+            uint32_t mean = 0u;
+            if (id == 1) {                                   // contrast: mean luma of the current image
+                if (threadIdx.x == 0) s_sum = 0ull;
+                __syncthreads();
+                unsigned long long local = 0ull;
+                for (uint32_t i = threadIdx.x; i < npx; i += blockDim.x)
+                    local += luma_of((uint32_t)cur[3u * i] | ((uint32_t)cur[3u * i + 1u] << 8) | ((uint32_t)cur[3u * i + 2u] << 16));
+                for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum, local);
+                __syncthreads();
+                mean = contrast_mean(s_sum, npx);
+            }
+            if (threadIdx.x < 256) s_lut[threadIdx.x] = (uint8_t)blend_u8(mean, threadIdx.x, alpha, clip);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < npx * 3u; i += blockDim.x) dst[i] = s_lut[cur[i]];
+        }
+        first = false;
+        __syncthreads();                                     // the next op reads what this one wrote (same CTA: block scope)
+    }
+    if (first && src != dst)                                 // no op applied: plain copy
+        for (uint32_t i = threadIdx.x; i < npx * 3u; i += blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t launch_color_jitter(const uint8_t* in, uint8_t* out, const void* recs, int batch, int H, int W, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    faa_color_jitter_kernel<<<(unsigned)batch, 1024, 0, stream>>>(in, out, reinterpret_cast<const JitterRec*>(recs), H, W);
+    return cudaGetLastError();
+}
+
+// Lighting (augmentations.py:197-215) sits between ToTensor and Normalize (data.py:70-72): x = u8/255 ; x += rgb[c] ;
+// (x - mean) / std - a per-IMAGE normalisation table [3][256] in fp32 with torch's operation order and IEEE division
+__global__ void faa_lighting_tables_kernel(const float* __restrict__ rgb, float* __restrict__ tabs, int n, float m0, float m1, float m2,
+                                           float s0, float s1, float s2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 768) return;
+    const int img = i / 768, e = i - img * 768, ch = e >> 8, u = e & 255;
+    const float mean = ch == 0 ? m0 : ch == 1 ? m1 : m2, sd = ch == 0 ? s0 : ch == 1 ? s1 : s2;
+    const float x = __fdiv_rn((float)u, 255.0f);
+    const float y = __fadd_rn(x, rgb[img * 3 + ch]);
+    tabs[i] = __fdiv_rn(__fadd_rn(y, -mean), sd);
+}
+
+cudaError_t launch_lighting_tables(const float* rgb, float* tabs, int n, const float mean[3], const float std[3], cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    faa_lighting_tables_kernel<<<(unsigned)((n * 768 + 255) / 256), 256, 0, stream>>>(rgb, tabs, n, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------

@@ -48,7 +48,8 @@ struct AugParams {
     const int32_t* order;       // [n_all] LPT schedule written by the resolve kernel, or nullptr
     const int32_t* n_heavy;     // device counters: schedule entries [0, n_heavy[0]) -> cluster kernel, [n_heavy[0], n_heavy[1]) -> mid
                                 // kernel (empty in a two-way split), rest -> light kernel; nullptr = no split
-    const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values
+    const float* norm_tab;      // [3][256] exact fp32 ToTensor+Normalize values ([n_all][3][256] when norm_stride != 0)
+    int32_t norm_stride;        // 768: one table per image (Lighting, augmentations.py:197-215); 0: one table per launch
     uint8_t* scratch;           // [n_all][H][W][3] uint8 scratch image for Sharpness->gather programs, or nullptr
     int32_t B, H, W, out_h, out_w;
     int32_t first;              // index of this launch's image 0 inside the n_all arrays
@@ -80,6 +81,9 @@ cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int b
 cudaError_t launch_mix_u8(const uint8_t* a, const uint8_t* b, const int32_t* partner, const int16_t* zb_a, const int16_t* zb_b,
                           const float* norm_tab, void* out, int batch, int H, int W, int dtype, float lam, float one_minus_lam,
                           cudaStream_t stream);
+
+cudaError_t launch_color_jitter(const uint8_t* in, uint8_t* out, const void* recs, int batch, int H, int W, cudaStream_t stream);
+cudaError_t launch_lighting_tables(const float* rgb, float* tabs, int n, const float mean[3], const float std[3], cudaStream_t stream);
 
 int pick_bands(int H, int W, int out_h, int out_w);
 void fill_geom(BandGeom& g, int bands, int H, int W, int out_h, int crop_pad, bool stage);

@@ -83,6 +83,77 @@ class CutoutDefault(object):
         return img
 
 
+_IMAGENET_PCA = {                                            # reference data.py:25-32
+    "eigval": [0.2175, 0.0188, 0.0045],
+    "eigvec": [[-0.5675, 0.7192, 0.4009], [-0.5808, -0.0045, -0.8140], [-0.5836, -0.6948, 0.4203]],
+}
+
+
+class Lighting(object):
+    """Drop-in for reference ``Lighting`` (augmentations.py:197-215): AlexNet-style PCA noise on a CHW float tensor,
+    between ToTensor and Normalize in the ImageNet chain (data.py:70-72).  In the batched path the per-image offsets
+    ``sample_rgb(n)`` go to ``augment_batch(..., lighting_rgb=...)``, which folds them into per-image normalisation tables."""
+
+    def __init__(self, alphastd, eigval=_IMAGENET_PCA["eigval"], eigvec=_IMAGENET_PCA["eigvec"]):
+        self.alphastd = alphastd
+        self.eigval = torch.Tensor(eigval)
+        self.eigvec = torch.Tensor(eigvec)
+
+    def _rgb(self, like):
+        alpha = like.new().resize_(3).normal_(0, self.alphastd)
+        return self.eigvec.type_as(like).clone().mul(alpha.view(1, 3).expand(3, 3)) \
+            .mul(self.eigval.view(1, 3).expand(3, 3)).sum(1).squeeze()
+
+    def __call__(self, img):
+        if self.alphastd == 0:
+            return img
+        rgb = self._rgb(img)
+        return img.add(rgb.view(3, 1, 1).expand_as(img))
+
+    def sample_rgb(self, n):
+        """[n, 3] fp32 offsets, drawn from torch's CPU generator exactly like n per-image calls of the reference."""
+        if self.alphastd == 0:
+            return torch.zeros(n, 3)
+        like = torch.empty(0)
+        return torch.stack([self._rgb(like) for _ in range(n)])
+
+
+class ColorJitter(object):
+    """torchvision ``ColorJitter(brightness, contrast, saturation)`` of the ImageNet train chain (reference data.py:65-69)
+    for uint8 NHWC CUDA batches: per image a random order (``torch.randperm(4)``) of Brightness / Contrast / Color
+    ``ImageEnhance`` blends with factors uniform in ``[max(0, 1 - x), 1 + x]`` - the arithmetic of the policy ops of the
+    same names (C ABI ``faa_color_jitter``)."""
+
+    def __init__(self, brightness=0.4, contrast=0.4, saturation=0.4):
+        self.ranges = [(max(0.0, 1.0 - v), 1.0 + v) if v else None for v in (brightness, contrast, saturation)]
+
+    def sample_parity(self, n):
+        """records of n images from torch's CPU generator in torchvision's order (get_params: randperm(4), then b, c, s)"""
+        recs = np.zeros(n, dtype=_lib.JITTER_DTYPE)
+        for i in range(n):
+            order = torch.randperm(4).tolist()
+            f = [None if r is None else float(torch.empty(1).uniform_(r[0], r[1])) for r in self.ranges]
+            recs[i]["order"] = [o if (o < 3 and f[o] is not None) else 3 for o in order]
+            recs[i]["alpha"] = [np.float32(x if x is not None else 1.0) for x in f]
+        return recs
+
+    def jitter_batch(self, batch_u8, recs=None, out=None):
+        """uint8 [B,H,W,3] CUDA -> uint8 [B,H,W,3] (``out`` may be the input itself)."""
+        if not (isinstance(batch_u8, torch.Tensor) and batch_u8.is_cuda and batch_u8.dtype == torch.uint8 and batch_u8.is_contiguous()):
+            raise ValueError("batch must be a contiguous uint8 CUDA tensor [B, H, W, 3]")
+        b, h, w, _ = batch_u8.shape
+        if recs is None:
+            recs = self.sample_parity(b)
+        d_recs = torch.from_numpy(np.ascontiguousarray(recs).view(np.uint8).reshape(-1).copy()).to(batch_u8.device)
+        if out is None:
+            out = torch.empty_like(batch_u8)
+        with torch.cuda.device(batch_u8.device):
+            import ctypes as C
+            _lib.check(_lib.lib.faa_color_jitter(batch_u8.data_ptr(), out.data_ptr(), b, h, w, d_recs.data_ptr(),
+                                                 C.c_void_p(torch.cuda.current_stream(batch_u8.device).cuda_stream)))
+        return out
+
+
 def policy_by_conf_name(aug):
     """conf['aug'] -> policy list, with the reference's error behaviour (data.py:85-109)."""
     if isinstance(aug, list):

@@ -221,7 +221,7 @@ def _stream_ptr(device):
 
 def augment_batch(policy: CompiledPolicy, batch_u8: torch.Tensor, tail: TailSpec, samples=None, boxes=None,
                   rng=None, out=None, partner=None, lam=1.0, pool=None, pool_samples=None, pool_boxes=None,
-                  first=0):
+                  first=0, lighting_rgb=None):
     """uint8 NHWC CUDA batch -> augmented NCHW ``tail.out_dtype`` (or uint8 NHWC).
 
     samples/boxes: resolved decisions (numpy structured arrays or CUDA uint8 tensors) - parity
@@ -245,6 +245,23 @@ def augment_batch(policy: CompiledPolicy, batch_u8: torch.Tensor, tail: TailSpec
     elif tuple(out.shape) != shape or out.dtype != tail.out_dtype or not out.is_contiguous():
         raise ValueError("out has the wrong shape/dtype")
 
+    if lighting_rgb is not None:
+        # Lighting (reference augmentations.py:197-215, between ToTensor and Normalize): per-image offsets [B,3] fp32
+        lighting_rgb = lighting_rgb.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(lighting_rgb.shape) != (B, 3):
+            raise ValueError("lighting_rgb must be [B, 3]")
+        policy._lighting_keep = lighting_rgb                 # stays alive until the launch has run
+        check(lib.faa_policy_set_lighting(policy.handle, lighting_rgb.data_ptr(), B))
+    try:
+        return _augment_launch(policy, batch_u8, tail, samples, boxes, rng, out, partner, lam, pool, pool_samples, pool_boxes,
+                               first, dev, B, H, W, t)
+    finally:
+        if lighting_rgb is not None:
+            check(lib.faa_policy_set_lighting(policy.handle, None, 0))
+
+
+def _augment_launch(policy, batch_u8, tail, samples, boxes, rng, out, partner, lam, pool, pool_samples, pool_boxes, first, dev,
+                    B, H, W, t):
     def to_dev(a, itemsize):
         if a is None:
             return None

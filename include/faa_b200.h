@@ -193,6 +193,21 @@ int faa_mix_u8(faa_policy_t* p, const uint8_t* d_a, const uint8_t* d_b, const in
                const int16_t* d_zero_box_a, const int16_t* d_zero_box_b, void* d_out, int batch, int h, int w,
                const faa_tail_t* tail, float lam, float one_minus_lam, void* stream);
 
+/* ---- ImageNet train chain pieces (data.py:60-73), "next" row N2 --------------------------------
+ * torchvision ColorJitter(brightness, contrast, saturation) (data.py:65-69) on uint8 HWC images, in place
+ * allowed (d_out == d_in): per image the ops of order[] (torch.randperm(4): 0 brightness, 1 contrast,
+ * 2 saturation, 3 hue = absent) with the factors alpha[] as PIL ImageEnhance blends - the arithmetic of
+ * the policy ops Brightness / Contrast / Color with per-image magnitudes. */
+typedef struct faa_jitter { float alpha[3]; uint8_t order[4]; } faa_jitter_t;
+int faa_color_jitter(const uint8_t* d_in, uint8_t* d_out, int batch, int h, int w,
+                     const faa_jitter_t* d_recs, void* stream);
+
+/* Lighting (augmentations.py:197-215) sits between ToTensor and Normalize (data.py:70-72):
+ * d_rgb [n][3] fp32 (device) = the per-image offsets eigvec . (alpha * eigval); subsequent faa_augment
+ * launches over n images normalise with per-image tables ((u8/255 + rgb[c]) - mean[c]) / std[c] in torch's
+ * fp32 operation order.  NULL switches it off again.  The array must stay valid until those launches ran. */
+int faa_policy_set_lighting(faa_policy_t* p, const float* d_rgb, int n);
+
 /* number of kernels this library has launched since load (bench bookkeeping) */
 uint64_t faa_launch_count(void);
 

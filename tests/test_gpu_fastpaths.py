@@ -17,10 +17,12 @@ import torch
 
 from helpers import ALL_OPS, exact_norm_table, seed_all, synth_batch
 
+from fast_autoaugment_b200 import _lib
 from fast_autoaugment_b200.engine import IMAGENET_MEAN, IMAGENET_STD, CIFAR_MEAN, CIFAR_STD, CompiledPolicy, TailSpec, augment_batch
 from oracle import pil_path
 
 pytestmark = pytest.mark.gpu
+_SAMPLE, _BOX = _lib.SAMPLE_DTYPE, _lib.BOX_DTYPE
 
 GEO = ["ShearX", "ShearY", "TranslateX", "TranslateY", "Rotate", "TranslateXAbs", "TranslateYAbs"]
 LUTS = ["Invert", "Solarize", "Posterize", "Brightness", "Posterize2"]
@@ -142,3 +144,67 @@ def test_mixup_of_augmented_u8_equals_the_fused_launch(shape, kind, dtype):
         plain = augment_batch(CompiledPolicy(pol.policies), x, tail, rng=make_rng(3, 2 * n, tail))
         ref = plain * np.float32(lam) + plain[perm.cuda()] * np.float32(1 - lam)
         assert torch.equal(data, ref)
+
+
+def test_color_jitter_matches_torchvision():
+    """row N2: ColorJitter(0.4, 0.4, 0.4) of the ImageNet train chain (reference data.py:65-69) - torchvision on PIL
+    images under the same torch seed is the oracle; bit-exact uint8"""
+    from torchvision import transforms
+    from fast_autoaugment_b200.data import ColorJitter
+    for shape in ((32, 32), (56, 104), (224, 224)):
+        n = 24
+        batch = synth_batch(n, shape, seed=shape[0])
+        tv = transforms.ColorJitter(brightness=0.4, contrast=0.4, saturation=0.4)
+        torch.manual_seed(17)
+        want = np.stack([np.asarray(tv(PIL.Image.fromarray(a))) for a in batch])
+        torch.manual_seed(17)
+        cj = ColorJitter(0.4, 0.4, 0.4)
+        recs = cj.sample_parity(n)
+        x = torch.from_numpy(batch).cuda()
+        got = cj.jitter_batch(x, recs).cpu().numpy()
+        bad = [i for i in range(n) if not np.array_equal(got[i], want[i])]
+        assert not bad, (shape, bad, recs[bad[:3]])
+        inplace = x.clone()
+        cj.jitter_batch(inplace, recs, out=inplace)
+        assert torch.equal(inplace.cpu(), torch.from_numpy(want))
+
+
+def test_lighting_folded_into_the_normalisation_matches_the_reference_chain():
+    """row N2: ToTensor -> Lighting(0.1, PCA) -> Normalize (reference data.py:70-72, augmentations.py:197-215) as
+    per-image normalisation tables; the reference's own Lighting class (oracle/_ref) or its restatement is the oracle"""
+    from torchvision import transforms
+    from fast_autoaugment_b200.data import Lighting, _IMAGENET_PCA
+    try:
+        from oracle import build_ref
+        mods = build_ref.import_ref()
+        RefLighting = mods[0].Lighting if mods is not None else Lighting
+    except Exception:
+        RefLighting = Lighting
+    n, shape = 40, (64, 72)
+    batch = synth_batch(n, shape, seed=4)
+    ref_chain = transforms.Compose([transforms.ToTensor(), RefLighting(0.1, _IMAGENET_PCA["eigval"], _IMAGENET_PCA["eigvec"]),
+                                    transforms.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)])
+    torch.manual_seed(5)
+    want = torch.stack([ref_chain(PIL.Image.fromarray(a)) for a in batch])
+    torch.manual_seed(5)
+    rgb = Lighting(0.1).sample_rgb(n)
+    pol = CompiledPolicy([[("Invert", 0.0, 0.0), ("Invert", 0.0, 0.0)]])
+    z = np.zeros(n, dtype=_SAMPLE)
+    zb = np.zeros((n, 2), dtype=_BOX)
+    x = torch.from_numpy(batch).cuda()
+    for split in ("0", "1000000000000"):
+        os.environ["FAA_SPLIT_MIN"] = split
+        got = augment_batch(pol, x, TailSpec(None, 0, False, IMAGENET_MEAN, IMAGENET_STD, 0, torch.float32), z, zb, lighting_rgb=rgb).cpu()
+        assert torch.equal(got, want), split
+    os.environ.pop("FAA_SPLIT_MIN", None)
+    # with a policy in front and a flip behind it: equals the un-lit launch re-normalised image by image
+    pol2 = CompiledPolicy([[("Rotate", 1.0, 0.3), ("Color", 1.0, 0.6)], [("AutoContrast", 1.0, 0.3), ("Sharpness", 1.0, 0.8)]])
+    seed_all(2)
+    s2, b2 = pol2.sample_parity(n, *shape, TailSpec.imagenet(0, torch.float32))
+    u8 = augment_batch(pol2, x, TailSpec(None, 0, True, IMAGENET_MEAN, IMAGENET_STD, 0, torch.uint8), s2, b2).cpu()
+    lit = augment_batch(pol2, x, TailSpec.imagenet(0, torch.float32), s2, b2, lighting_rgb=rgb).cpu()
+    m, sd = torch.tensor(IMAGENET_MEAN).view(3, 1, 1), torch.tensor(IMAGENET_STD).view(3, 1, 1)
+    for i in range(n):
+        t = u8[i].permute(2, 0, 1).float().div(255)
+        t = t.add(rgb[i].view(3, 1, 1).expand_as(t))
+        assert torch.equal(lit[i], (t - m) / sd), i

@@ -17,7 +17,10 @@ pairs = [[(a, 1.0, rng.random()), (b, 1.0, rng.random())] for a in ALL_OPS for b
 singles = [[(a, 1.0, rng.random()), (a, 0.0, 0.5)] for a in ALL_OPS]
 pol = CompiledPolicy(pairs + singles)
 n = pol.n_sub
-for shape, split in (((48, 64), "0"), ((224, 224), "0"), ((40, 56), "1000000000000")):
+CASES = (((48, 64), "0"), ((224, 224), "0"), ((40, 56), "1000000000000"))
+U8_ONLY = "u8only" in sys.argv          # diagnostic: only the uint8 launch of the 224x224 case
+if U8_ONLY: CASES = CASES[1:2]
+for shape, split in CASES:
     os.environ["FAA_SPLIT_MIN"] = split
     x = torch.from_numpy(synth_batch(n, shape, seed=1)).cuda()
     s = np.zeros(n, dtype=np.dtype([("sub", "<u2"), ("gate", "u1"), ("sign", "u1"), ("crop_dy", "i1"), ("crop_dx", "i1"), ("flip", "u1"),
@@ -25,11 +28,12 @@ for shape, split in (((48, 64), "0"), ((224, 224), "0"), ((40, 56), "10000000000
     s["sub"] = np.arange(n); s["gate"] = 3; s["flip"] = np.arange(n) & 1; s["sign"] = (np.arange(n) >> 1) & 3
     b = np.zeros((n, 2), dtype=np.dtype([("x0", "<i2"), ("y0", "<i2"), ("x1", "<i2"), ("y1", "<i2")]))
     b["x0"] = 3; b["y0"] = 5; b["x1"] = shape[1] // 2; b["y1"] = shape[0] // 2
-    for dt in (torch.float16, torch.float32):
+    for dt in (() if U8_ONLY else (torch.float16, torch.float32)):
         out = augment_batch(pol, x, TailSpec(None, 0, True, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), 8, dt), s, b)
     out = augment_batch(pol, x, TailSpec.raw_u8(), s, b)
     torch.cuda.synchronize()
     print("ok", shape, split, float(out.float().mean()), flush=True)
+if U8_ONLY: sys.exit(0)
 os.environ["FAA_SPLIT_MIN"] = "0"
 p2 = CompiledPolicy(archive.fa_resnet50_rimagenet())
 tail = TailSpec.imagenet(0, torch.float16)
