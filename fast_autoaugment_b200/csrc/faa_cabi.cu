@@ -211,6 +211,8 @@ struct faa_policy {
     uint64_t last_first_index = 0; bool have_last = false; AheadKey last_key{};
     cudaStream_t ahead_stream = nullptr; cudaEvent_t ev_ahead = nullptr;
     void* d_scratch = nullptr; size_t d_scratch_bytes = 0;   // Sharpness->gather scratch images
+    uint32_t done_target[2] = {0, 0};    // persistent chained steps: CTAs that have been launched on each program slot so far
+    int sm_count = 0;
     bool has_sg = false;                 // some sub-policy has Sharpness followed by a geometric op
     void* d_in = nullptr; size_t d_in_bytes = 0;
     void* d_out = nullptr; size_t d_out_bytes = 0;
@@ -610,6 +612,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             CK(cudaMemset(p->d_order, 0, 2 * (4 * (need / sizeof(Prog)) * sizeof(int32_t) + 32)));
             p->d_progs_bytes = need;
             p->ahead_valid = false;
+            p->done_target[0] = p->done_target[1] = 0;      // (the completion counters live in d_order and start at zero)
         }
     }
     // geometry of the pixel launch (needed by the resolve step: allow_mat)
@@ -721,8 +724,16 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         }
     };
     // scratch images: Sharpness -> gather programs of the cluster kernel, every Sharpness-first two-op program of the mid kernel
+    // Persistent mid / light kernels (chained schedule only; FAA_PERSIST=0 keeps one CTA row per image): rows loop over
+    // their entries, all CTAs of a kernel are resident at once, so it releases its dependents immediately and consecutive
+    // kernels - and steps - overlap for their whole length.  What the early release no longer orders is ordered explicitly:
+    // program slots by completion counters the next resolve kernel of the slot waits for, scratch images by a copy per slot.
+    static const bool persist_off = [] { const char* e = getenv("FAA_PERSIST"); return e && e[0] == '0'; }();
+    const bool persist = use_chain && !persist_off;
+    size_t scratch_slot_bytes = 0;
     if ((p->has_sg || use_mid) && !d_partner && (w & 3) == 0) {
-        const size_t need = (size_t)n_all * img_bytes;
+        scratch_slot_bytes = (size_t)n_all * img_bytes;
+        const size_t need = scratch_slot_bytes * (persist ? 2 : 1);
         if (p->d_scratch_bytes < need) {
             if (p->d_scratch) { CK(cudaStreamSynchronize(stream)); CK(cudaFree(p->d_scratch)); p->d_scratch = nullptr; p->d_scratch_bytes = 0; }
             CK(cudaMalloc(&p->d_scratch, need));
@@ -787,7 +798,12 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         bool overlap_ok = p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
                           !overlap(out0, out1, p->prev_out) && !overlap(out0, out1, p->prev_in);
         AugParams Pc = P;
-        Pc.chain = 1; Pc.pdl = 0;
+        Pc.chain = persist ? 2 : 1; Pc.pdl = 0;
+        // completion counter of a slot: the first spare word behind its order / counters / ready arrays
+        auto done_word = [&](int s) { return reinterpret_cast<uint32_t*>(reinterpret_cast<int32_t*>(p->d_order) + (size_t)s * (4 * cap_imgs + 8) + 4 * cap_imgs); };
+        auto wait_for_slot = [&](int s, ResolveParams& r) {
+            r.wait_done = persist ? done_word(s) : nullptr; r.wait_target = p->done_target[s];
+        };
         if (hit) {
             slot = p->ahead_slot;
             Pc.ticket = p->ahead_ticket;
@@ -796,6 +812,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             bind_slot(slot, R, &Pc);
             R.ticket = ++p->ticket; R.pdl = overlap_ok ? 1 : 0;
             Pc.ticket = R.ticket;
+            wait_for_slot(slot, R);
             CK(launch_resolve(R, stream));
             g_launches++;
             overlap_ok = true;                              // the kernels behind it may overlap IT
@@ -814,20 +831,44 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
             bind_slot(slot ^ 1, R2, nullptr);
             R2.ticket = ++p->ticket; R2.pdl = overlap_ok ? 1 : 0;
             // (its slot's last readers - the step before this one - copied their programs before they let any
-            //  later kernel of the stream start, so the resolve kernel may overwrite the slot as soon as it runs)
+            //  later kernel of the stream start, so the resolve kernel may overwrite the slot as soon as it runs;
+            //  persistent readers release their dependents at once and are waited for through the slot's counter)
+            wait_for_slot(slot ^ 1, R2);
             CK(launch_resolve(R2, stream));
             g_launches++;
             p->ahead_key = key; p->ahead_key.first_index = rng->first_index + stride;
             p->ahead_slot = slot ^ 1; p->ahead_valid = true; p->ahead_ticket = R2.ticket;
         }
+        if (persist) {
+            if (!p->sm_count) CK(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+            Pc.done = done_word(slot);
+            if (P.scratch) Pc.scratch = P.scratch + (size_t)slot * scratch_slot_bytes;
+        }
         AugParams Pm = Pc;                                  // the mid kernel: its own (taller) bands in bands / geo[0]
         if (use_mid) set_mid_geometry(Pm);
+        if (persist) {
+            // one resident wave each (launch bounds: light CTAs / SM, 2 mid CTAs / SM)
+            static const int rows_l = [] { const char* e = getenv("FAA_ROWS_LIGHT"); return e ? atoi(e) : 0; }();
+            static const int rows_m = [] { const char* e = getenv("FAA_ROWS_MID"); return e ? atoi(e) : 0; }();
+            const int lb = P.geo[1].bands > 0 ? P.geo[1].bands : 1;
+            Pc.grid_y = rows_l > 0 ? rows_l : (p->sm_count * resident_ctas_per_sm(1)) / lb;
+            // (mid rows: ONE CTA per SM measured best - 58.1 us vs 58.9 us with both slots - the light CTAs that follow
+            //  share the SM with it from the start; profiles/r02_schedules.txt)
+            Pm.grid_y = rows_m > 0 ? rows_m : p->sm_count / (Pm.bands > 0 ? Pm.bands : 1);
+            if (Pc.grid_y < 1) Pc.grid_y = 1;
+            if (Pm.grid_y < 1) Pm.grid_y = 1;
+        }
         const int order3[3] = {chain_mode == 2 ? 1 : 0, 2, chain_mode == 2 ? 0 : 1};   // default: cluster, mid, light
         for (int k = 0; k < 3; ++k) {
             const int which = order3[k];
-            if (which == 2) { if (use_mid) { CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, stream)); g_launches++; } }
+            if (which == 2) { if (use_mid) { CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, stream)); g_launches++; if (persist) p->done_target[slot] += augment_cta_count(Pm, 2); } }
             else if (which == 0 && no_heavy) continue;
-            else { CK(launch_augment(Pc, tail->out_dtype, use_tab, which, stream)); g_launches++; }
+            else {
+                AugParams Pk = Pc;
+                if (which == 0) Pk.grid_y = 0;              // the cluster kernel keeps one cluster per entry
+                CK(launch_augment(Pk, tail->out_dtype, use_tab, which, stream)); g_launches++;
+                if (persist) p->done_target[slot] += augment_cta_count(Pk, which);
+            }
         }
         p->chain_live = true; p->chain_stream = stream;
         p->prev_in[0] = in0; p->prev_in[1] = in1; p->prev_out[0] = out0; p->prev_out[1] = out1;

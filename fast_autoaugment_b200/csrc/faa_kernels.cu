@@ -41,6 +41,19 @@ namespace cg = cooperative_groups;
 
 namespace faa {
 
+// Opaque re-reads.  The mid and light kernels run their per-entry body inside a loop (persistent rows); everything in the
+// body that only depends on the thread index or on constants (index arithmetic, peer shared-memory addresses) is
+// loop-invariant, gets hoisted in front of the loop and then lives across the whole body: ~45 spilled registers at the
+// 48 / 64-register budgets.  Reading the thread index through a volatile asm per use (an S2R where it is used, as in
+// straight-line code) and passing cluster ranks through opaque_u32 keeps those computations where they are written.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+struct OpaqueTid {
+    struct X { __device__ __forceinline__ operator unsigned() const { unsigned t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; } } x;
+};
+}  // namespace faa
+#define threadIdx (::faa::OpaqueTid{})
+namespace faa {
+
 constexpr int kThreads = 256;
 constexpr int kMaxDevices = 64;
 #ifndef FAA_MIN_CTAS
@@ -84,6 +97,10 @@ __global__ void __launch_bounds__(1024) faa_resolve_kernel(const __grid_constant
     // let the dependent pixel kernel start launching (its prologue overlaps this kernel)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x < 3 * kCostBuckets) s_count[threadIdx.x] = 0;
+    if (P.wait_done != nullptr && threadIdx.x == 0) {            // the slot's previous readers (persistent pixel kernels) are done
+        uint32_t v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.wait_done) : "memory"); } while ((int32_t)(v - P.wait_target) < 0);
+    }
     __syncthreads();
     for (int t = threadIdx.x; t < P.n; t += blockDim.x) {
         const int i = P.first + t;
@@ -185,6 +202,17 @@ __device__ __forceinline__ void wait_ticket(const int32_t* ready, int32_t ticket
         do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory"); } while (v != ticket);
     }
     __syncthreads();
+}
+
+// persistent launches: schedule row y of grid_y visits entries y, 2*grid_y-1-y, 2*grid_y+y, ... of its (cost-sorted)
+// segment - the row that drew the most expensive entry of one round gets the cheapest of the next
+__device__ __forceinline__ int sched_entry(int k, int y, int gy) { return k * gy + ((k & 1) ? gy - 1 - y : y); }
+
+// a finished CTA counts itself: the resolve kernel that rewrites this slot's programs waits for the total
+__device__ __forceinline__ void count_done(uint32_t* done) {
+    if (done == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done) : "memory");
 }
 
 // the byte range of image rows a CTA may touch through the band-local paths
@@ -304,11 +332,11 @@ static __device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool wan
                     // all remote loads in flight together (each is a ~200-cycle DSMEM round trip)
                     uint32_t v[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) v[r] = r < bands ? cluster.map_shared_rank(&st.hist[j][0], r)[bin] : 0u;
+                    for (int r = 0; r < 8; ++r) v[r] = r < bands ? cluster.map_shared_rank(&st.hist[j][0], opaque_u32(r))[bin] : 0u;
                     const uint32_t t = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 #pragma unroll
                     for (int r = 0; r < 8; ++r)
-                        if (r < bands) cluster.map_shared_rank(&st.tot[0], r)[bin] = t;
+                        if (r < bands) cluster.map_shared_rank(&st.tot[0], opaque_u32(r))[bin] = t;
                 }
             }
         } else {
@@ -320,7 +348,7 @@ static __device__ uint32_t exchange_stats(int bands, uint32_t n_pixels, bool wan
         if (bands > 1) {
             unsigned long long v[8];                                // all remote loads in flight together
 #pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = r < bands ? *cluster.map_shared_rank(&st.suml[j], r) : 0ull;
+            for (int r = 0; r < 8; ++r) v[r] = r < bands ? *cluster.map_shared_rank(&st.suml[j], opaque_u32(r)) : 0ull;
             t = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
         } else {
             t = st.suml[j];
@@ -1222,7 +1250,7 @@ __device__ void build_scalar_stats_table(const AugParams& P, const float* s_norm
         uint32_t v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r)                                        // remote loads in flight together
-            v[r] = r < bands ? (bands > 1 ? cluster.map_shared_rank(&st.xpart[0], r)[j] : st.xpart[j]) : (j < 3 ? 255u : 0u);
+            v[r] = r < bands ? (bands > 1 ? cluster.map_shared_rank(&st.xpart[0], opaque_u32(r))[j] : st.xpart[j]) : (j < 3 ? 255u : 0u);
         uint32_t t;
         if (j < 3) t = min(min(min(v[0], v[1]), min(v[2], v[3])), min(min(v[4], v[5]), min(v[6], v[7])));
         else if (j < 6) t = max(max(max(v[0], v[1]), max(v[2], v[3])), max(max(v[4], v[5]), max(v[6], v[7])));
@@ -1231,7 +1259,7 @@ __device__ void build_scalar_stats_table(const AugParams& P, const float* s_norm
         if (j == 6) {                                                      // 64-bit luma total
             unsigned long long tot = 0;
             for (int r = 0; r < bands; ++r) {
-                const uint32_t* xp = bands > 1 ? cluster.map_shared_rank(&st.xpart[0], r) : &st.xpart[0];
+                const uint32_t* xp = bands > 1 ? cluster.map_shared_rank(&st.xpart[0], opaque_u32(r)) : &st.xpart[0];
                 tot += (unsigned long long)xp[6] | ((unsigned long long)xp[7] << 32);
             }
             st.xtot[6] = (uint32_t)tot; st.xtot[7] = (uint32_t)(tot >> 32);
@@ -1268,7 +1296,7 @@ __device__ void build_scalar_stats_table(const AugParams& P, const float* s_norm
 // ---------------------------------------------------------------------------------------
 // launch 2
 template <int OUT, int NSRC, bool TAB>
-__global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
+static __device__ __forceinline__ void cluster_kernel_body(const AugParams& P) {
     extern __shared__ __align__(128) uint8_t s_dyn[];           // NSRC staged row bands [+ materialisation chunk]
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ImgState st[NSRC];
@@ -1393,6 +1421,12 @@ __device__ __forceinline__ void inplace_pointwise(const AugParams& P, uint8_t* b
     }
 }
 
+template <int OUT, int NSRC, bool TAB>
+__global__ void __launch_bounds__(kThreads, (NSRC == 1 ? FAA_MIN_CTAS : 2)) faa_augment_kernel(const __grid_constant__ AugParams P) {
+    cluster_kernel_body<OUT, NSRC, TAB>(P);
+    count_done(P.done);                                          // (CTAs without an entry included)
+}
+
 // ---------------------------------------------------------------------------------------
 // launch 2b: the "mid" kernel of a three-way split: statistics -> per-channel LUT programs (AutoContrast, Equalize,
 // Contrast, with static LUT partners) and Sharpness (+ static LUT).  One cluster per image like the cluster kernel
@@ -1411,15 +1445,25 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
     __shared__ __align__(16) uint32_t s_tile[(kMidThreadsMax / 32) * 128];      // gather tiles (128 px per warp)
     __shared__ __align__(8) uint64_t s_bar;
 
-    const int band = blockIdx.x;
-    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
-    const uint32_t s_lo = P.geo[0].lo[band], s_len = P.geo[0].len[band];
     if (TAB && !P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
-    const int e0 = ld_sched(P.n_heavy, P.chain), e1 = ld_sched(P.n_heavy + 1, P.chain);
-    if ((int)blockIdx.y >= e1 - e0) return;                      // cluster-uniform
-    const int img = ld_sched(P.order + P.first + e0 + blockIdx.y, P.chain);
+    if (P.chain == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // persistent: see count_done
+    const int e0 = ld_sched(P.n_heavy, P.chain), n_ent = ld_sched(P.n_heavy + 1, P.chain) - e0;
+    // One entry per row, or a persistent row's entries.  The body is written for ONE entry; so that the compiler does not
+    // hoist its loop-invariant parts (thread-index arithmetic, peer addresses) in front of the loop, where they would live
+    // across the whole body and spill, thread and band indices are re-read opaquely per use (threadIdx macro above).
+    for (int round = 0;; ++round) {
+    const int ent = sched_entry(round, (int)blockIdx.y, (int)gridDim.y);
+    if (ent >= n_ent) break;                                     // cluster-uniform
+    if (round) {                                                 // shared memory (and the staging buffer, for the TMA) is free again
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+    const int band = (int)opaque_u32(blockIdx.x);
+    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
+    const uint32_t s_lo = P.geo[0].lo[band], s_len = P.geo[0].len[band];
+    const int img = ld_sched(P.order + P.first + e0 + ent, P.chain);
     const int idx = P.first + img;
     if (TAB && P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + (size_t)idx * P.norm_stride + i);
@@ -1427,7 +1471,7 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
     if (threadIdx.x < sizeof(Prog) / 4)
         reinterpret_cast<uint32_t*>(&st.prog)[threadIdx.x] = ld_sched(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x, P.chain);
     __syncthreads();
-    if (P.chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied
+    if (P.chain == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied
     if (s_len) mbar_wait(&s_bar, 0);
 
     const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
@@ -1565,6 +1609,8 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
         if (peers_pending) cluster_wait();                       // peers have read this CTA's statistics record
     }
     zero_box_rows<OUT>(P, st.prog, out_img, oy0, oy1);
+    }   // rounds
+    count_done(P.done);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1572,7 +1618,7 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
 // PLAIN / LUT / POINT / GEOM classes only - no cluster, 3 KB of static shared memory, a fraction of
 // the cluster kernel's registers and code.  It owns schedule entries [n_heavy, B).
 #ifndef FAA_LIGHT_CTAS
-#define FAA_LIGHT_CTAS 5
+#define FAA_LIGHT_CTAS 4
 #endif
 template <int OUT, bool TAB>
 __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_kernel(const __grid_constant__ AugParams P) {
@@ -1585,15 +1631,22 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar;
 
-    const int band = blockIdx.x;
-    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
-    const uint32_t s_lo = P.geo[1].lo[band], s_len = P.geo[1].len[band];
     if (TAB && !P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + i);
     wait_ticket(P.ready, P.ticket);
+    if (P.chain == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // persistent: see count_done
     const int n_heavy = ld_sched(P.n_heavy + 1, P.chain);       // entries in front of the light segment (heavy + mid)
-    if ((int)blockIdx.y >= P.B - n_heavy) return;
-    const int img = ld_sched(P.order + P.first + n_heavy + blockIdx.y, P.chain);     // uniform load per warp
+    for (int round = 0;; ++round) {                              // one entry per row, or a persistent row's entries (see the mid kernel)
+    const int ent = sched_entry(round, (int)blockIdx.y, (int)gridDim.y);
+    if (ent >= P.B - n_heavy) break;
+    if (round) {                                                 // shared memory (and the staging buffer, for the TMA) is free again
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+    const int band = (int)opaque_u32(blockIdx.x);
+    const uint32_t img_bytes = (uint32_t)P.H * (uint32_t)P.W * 3u;
+    const uint32_t s_lo = P.geo[1].lo[band], s_len = P.geo[1].len[band];
+    const int img = ld_sched(P.order + P.first + n_heavy + ent, P.chain);     // uniform load per warp
     const int idx = P.first + img;
     if (TAB && P.norm_stride)
         for (int i = threadIdx.x; i < 768; i += blockDim.x) s_norm[i] = __ldg(P.norm_tab + (size_t)idx * P.norm_stride + i);
@@ -1601,7 +1654,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     if (threadIdx.x < sizeof(Prog) / 4)
         reinterpret_cast<uint32_t*>(&s_prog)[threadIdx.x] = ld_sched(reinterpret_cast<const uint32_t*>(P.progs + idx) + threadIdx.x, P.chain);
     __syncthreads();
-    if (P.chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied: see the cluster kernel
+    if (P.chain == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // program copied: see the cluster kernel
     const uint32_t lut_mask = s_prog.lut_mask;
     if (lut_mask) {                                   // static LUTs only (no statistics in light programs)
 #pragma unroll
@@ -1692,6 +1745,8 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
         }
     }
     zero_box_rows<OUT>(P, s_prog, out_img, oy0, oy1);
+    }   // rounds
+    count_done(P.done);
 }
 
 #ifndef FAA_TU_OUT
@@ -1985,6 +2040,8 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     return cudaLaunchKernelEx(&cfg, faa_augment_kernel<OUT, NSRC, TAB>, p);
 }
 
+static inline int rows_of(const AugParams& p) { return (p.grid_y > 0 && p.grid_y < p.B) ? p.grid_y : p.B; }
+
 template <int OUT, bool TAB>
 static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
     const size_t dyn = (size_t)p.geo[1].band_cap;
@@ -1999,7 +2056,7 @@ static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
         configured[dev] = dyn;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)p.geo[1].bands, (unsigned)p.B, 1);
+    cfg.gridDim = dim3((unsigned)p.geo[1].bands, (unsigned)rows_of(p), 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
@@ -2031,7 +2088,7 @@ static cudaError_t launch_mid(const AugParams& p, cudaStream_t stream) {
                                             return (v == 128 || v == 256 || v == 512) ? v : 0; }();
         // enough threads for the band: 512 for the tall bands of large images, 256 otherwise
         const int threads = mid_threads ? mid_threads : ((size_t)p.geo[0].band_cap > 48 * 1024 ? 512 : 256);
-        cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
+        cfg.gridDim = dim3((unsigned)p.bands, (unsigned)rows_of(p), 1);
         cfg.blockDim = dim3((unsigned)threads, 1, 1);
         cfg.dynamicSmemBytes = dyn;
         cfg.stream = stream;
@@ -2080,6 +2137,15 @@ cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, int w
     case OUT_U8_HWC: return launch_out<OUT_U8_HWC>(p, false, false, which, stream);
     default: return cudaErrorInvalidValue;
     }
+}
+
+int resident_ctas_per_sm(int which) { return which == 1 ? FAA_LIGHT_CTAS : which == 2 ? 2 : FAA_MIN_CTAS; }
+
+unsigned augment_cta_count(const AugParams& p, int which) {
+    if (p.B <= 0) return 0u;
+    if (which == 1) return (unsigned)p.geo[1].bands * (unsigned)rows_of(p);
+    if (which == 2) return (unsigned)p.bands * (unsigned)rows_of(p);
+    return (unsigned)p.bands * (unsigned)p.B;
 }
 
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream) {

@@ -27,6 +27,8 @@ struct ResolveParams {
     int32_t* ready;             // optional: set to `ticket` (release) once programs / order / n_heavy are written
     int32_t ticket;
     int32_t pdl;                // launch with programmatic stream serialization (chained steps)
+    const uint32_t* wait_done;  // optional: before writing anything, spin until *wait_done has reached wait_target (the pixel
+    uint32_t wait_target;       // CTAs that read this slot's previous programs count themselves there when they finish)
 };
 cudaError_t launch_resolve(const ResolveParams& p, cudaStream_t stream);
 
@@ -70,9 +72,17 @@ struct AugParams {
     int32_t chain;              // 1: steps are chained with programmatic dependent launches on ONE stream - no
                                 // griddepcontrol.wait (nothing of the previous kernel is consumed), trigger the
                                 // dependents once this CTA has copied its program
+                                // 2: same, with persistent mid / light kernels - the dependents are released at once and
+                                // the slot's next writer waits for `done` instead
+    int32_t grid_y;             // > 0: launch this many schedule rows (CTAs / clusters per band); each one loops over the
+                                // entries row, row + grid_y, ... of its segment.  0: one row per image (B)
+    uint32_t* done;             // optional completion counter: every CTA adds 1 when it has finished (release)
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };
+// number of CTAs launch_augment starts for (p, which): what `done` advances by
+unsigned augment_cta_count(const AugParams& p, int which);
+int resident_ctas_per_sm(int which);     // the launch bounds of the light (1) / mid (2) / cluster (0) kernel
 cudaError_t launch_augment(const AugParams& p, int out_type, bool use_tab, int which, cudaStream_t stream);   // which: 0 cluster, 1 light, 2 mid
 
 cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int batch, int64_t n_per_sample,

@@ -1,4 +1,5 @@
 #!/bin/bash
-for e in "FAA_X=0" "FAA_CHAIN=1" "FAA_X=0" "FAA_CHAIN=1" "FAA_CHAIN=2" "FAA_CHAIN=1 FAA_MID_BANDS=4 FAA_MID_THREADS=256"; do
-  env $e python tools/mix_probe.py
+# schedule comparison on the headline policy mix (tools/mix_probe.py): event schedule, chained, chained + persistent rows
+for e in "FAA_CHAIN=0" "FAA_PERSIST=0" "FAA_PERSIST=1" "FAA_PERSIST=1 FAA_ROWS_MID=74" "FAA_PERSIST=1 FAA_ROWS_MID=111" "FAA_PERSIST=1 FAA_ROWS_LIGHT=63" "FAA_PERSIST=1 FAA_ROWS_LIGHT=105"; do
+  env $e timeout 120 python tools/mix_probe.py
 done
