@@ -201,6 +201,7 @@ struct faa_policy {
     float* d_norm = nullptr;            // [3][256]
     float norm_mean[3] = {-1e30f, 0, 0}, norm_std[3] = {0, 0, 0};
     float norm_host[768];
+    bool fma_known[2] = {false, false}, fma_ok[2] = {false, false};   // [fp16, bf16]: does fmaf(u, scale, bias) round like the table?
     // scratch of faa_augment_host
     void* d_progs = nullptr; size_t d_progs_bytes = 0;
     void* d_order = nullptr;             // int32 [capacity of d_progs in images] (+ counters), two slots like d_progs
@@ -521,16 +522,24 @@ static int normalisation(faa_policy* p, const faa_tail_t* tail, AugParams& P, bo
         CK(cudaMemcpyAsync(p->d_norm, p->norm_host, 768 * sizeof(float), cudaMemcpyHostToDevice, stream));
     }
     P.norm_tab = p->d_norm;
-    bool fma_ok = tail->out_dtype == FAA_F16 || tail->out_dtype == FAA_BF16;
+    if (!same) p->fma_known[0] = p->fma_known[1] = false;
+    const bool half_out = tail->out_dtype == FAA_F16 || tail->out_dtype == FAA_BF16;
+    const int slot = tail->out_dtype == FAA_BF16 ? 1 : 0;
+    bool fma_ok = half_out;
     for (int c = 0; c < 3; ++c) {
         double sc = 1.0 / (255.0 * (double)tail->std[c]);
         double bi = -(double)tail->mean[c] / (double)tail->std[c];
         P.scale[c] = (float)sc; P.bias[c] = (float)bi;
-        if (fma_ok)
+    }
+    if (half_out && p->fma_known[slot]) {
+        fma_ok = p->fma_ok[slot];                           // (768 conversions per call are a visible part of a small step)
+    } else if (half_out) {
+        for (int c = 0; c < 3 && fma_ok; ++c)
             for (int u = 0; u < 256 && fma_ok; ++u) {
                 float f = fmaf((float)u, P.scale[c], P.bias[c]);
                 if (bits16(tail->out_dtype, f) != bits16(tail->out_dtype, p->norm_host[c * 256 + u])) fma_ok = false;
             }
+        p->fma_known[slot] = true; p->fma_ok[slot] = fma_ok;
     }
     use_tab = !fma_ok;
     return FAA_OK;
@@ -698,7 +707,11 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     // two-stream schedule with events (light kernel on the caller's stream, cluster kernel on a priority stream).
     int chain_mode = 1;                                   // measured (profiles/r02_schedules.txt): 62.4 us chained vs 65.6 us with events
     if (const char* e = getenv("FAA_CHAIN")) chain_mode = atoi(e);
-    const bool use_chain = chain_mode != 0 && use_split && allow_ahead && rng && !d_samples && !d_partner &&
+    // (launches too small to split are chained as well: resolve(N+1), cluster(N) - their step is bound by kernel latencies,
+    //  which only overlap across steps on one stream; uint8 output stays on the event schedule)
+    static const bool chain_small_off = [] { const char* e = getenv("FAA_CHAIN_SMALL"); return e && e[0] == '0'; }();
+    const bool chain_small = !use_split && !chain_small_off && use_order && tail->out_dtype != FAA_U8_HWC;
+    const bool use_chain = chain_mode != 0 && (use_split || chain_small) && allow_ahead && rng && !d_samples && !d_partner &&
                            !(getenv("FAA_AHEAD") && getenv("FAA_AHEAD")[0] == '0');
     // Three-way split: statistics-LUT and Sharpness programs run in the lean mid kernel.
     // Needs the geometry its paths assume: float planes of the image's own size, no crop, W % 4 == 0, staged bands.
@@ -767,6 +780,39 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     // fused Mixup mixes the fp32 normalised values before the output rounding: the fma shortcut is only proven to round
     // like the exact value for a DIRECT fp16 / bf16 store, so two-source launches always take the exact table
     if (d_partner) use_tab = true;
+    // Self-resolving launch (FAA_SELF=0 turns it off): a launch too small to split is bound by kernel latencies and by the
+    // host's launch rate, not by bytes.  Thread 0 of every CTA draws its image's decisions and builds the program itself
+    // (same Philox counters, same build_prog): ONE kernel per step, no program array, no ticket - consecutive steps have
+    // no dependency left and overlap through programmatic dependent launch.
+    static const bool self_off = [] { const char* e = getenv("FAA_SELF"); return e && e[0] == '0'; }();
+    if (!use_split && !self_off && rng && !d_samples && !d_partner) {
+        const uintptr_t in0 = (uintptr_t)d_in_all + (in_mod ? 0 : (size_t)first * img_bytes),
+                        in1 = in0 + (size_t)(in_mod ? in_mod : batch) * img_bytes;
+        const uintptr_t out0 = (uintptr_t)d_out, out1 = out0 + (size_t)batch * tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
+        auto overlap = [](uintptr_t a0, uintptr_t a1, const uintptr_t b[2]) { return a0 < b[1] && b[0] < a1; };
+        const bool overlap_ok = p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
+                                !overlap(out0, out1, p->prev_out) && !overlap(out0, out1, p->prev_in) && !P.norm_stride;
+        AugParams Ps = P;
+        Ps.progs = nullptr; Ps.order = nullptr; Ps.n_heavy = nullptr; Ps.ready = nullptr; Ps.done = nullptr; Ps.grid_y = 0;
+        Ps.self_resolve = 1;
+        Ps.sr_ops = d_ops; Ps.sr_probs = p->d_probs; memcpy(&Ps.sr_rng, rng, sizeof(RngCfg));
+        Ps.sr_n_sub = p->n_sub; Ps.sr_n_op = p->n_op; Ps.sr_op_base = op_base; Ps.sr_apply_tail = apply_tail; Ps.sr_allow = R.allow;
+        // chain = 1: no griddepcontrol.wait (nothing of the previous kernel is consumed), dependents released once the CTA has
+        // its program; a step that touches the previous step's buffers is launched as a plain stream-ordered kernel instead
+        Ps.chain = overlap_ok ? 1 : 0; Ps.pdl = 0;
+        // tiny images (CIFAR): Sharpness -> gather programs are evaluated lazily instead of through the scratch image - the
+        // last thing consecutive steps shared - and every CTA releases the next step at once (chain = 3)
+        if ((size_t)h * w <= 4096) {
+            Ps.sr_allow &= ~2; Ps.scratch = nullptr;
+            if (overlap_ok) Ps.chain = 3;
+        }
+        CK(launch_augment(Ps, tail->out_dtype, use_tab, 0, stream));
+        g_launches++;
+        p->ahead_valid = false;
+        p->chain_live = true; p->chain_stream = stream;
+        p->prev_in[0] = in0; p->prev_in[1] = in1; p->prev_out[0] = out0; p->prev_out[1] = out1;
+        return FAA_OK;
+    }
     // resolve-ahead: did the previous call already resolve exactly this batch on the side stream?
     const bool spec_ok = allow_ahead && !ahead_off && rng && !d_samples && !d_partner;
     faa_policy::AheadKey key; memset(&key, 0, sizeof key);
@@ -861,6 +907,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         const int order3[3] = {chain_mode == 2 ? 1 : 0, 2, chain_mode == 2 ? 0 : 1};   // default: cluster, mid, light
         for (int k = 0; k < 3; ++k) {
             const int which = order3[k];
+            if (which != 0 && !use_split) continue;          // one pixel kernel
             if (which == 2) { if (use_mid) { CK(launch_augment(Pm, tail->out_dtype, use_tab, 2, stream)); g_launches++; if (persist) p->done_target[slot] += augment_cta_count(Pm, 2); } }
             else if (which == 0 && no_heavy) continue;
             else {
@@ -982,6 +1029,21 @@ int faa_augment(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, in
         return fail(FAA_ERR_VALUE, "intermediate launches of a chained policy must write uint8 HWC at the input size");
     return augment_common(p, d_in, batch, 0, d_out, batch, h, w, tail, d_samples, d_boxes, rng, op_base, nullptr,
                           1.0f, 0.0f, apply_tail, p->n_op <= FAA_MAX_FUSED_OPS, stream);
+}
+
+int faa_augment_many(faa_policy_t* p, int n_steps, const uint8_t* const* d_in, void* const* d_out, int batch, int h, int w,
+                     const faa_tail_t* tail, const faa_rng_t* rng, uint64_t index_stride, void* stream) {
+    if (!p || !rng || !d_in || !d_out) return fail(FAA_ERR_VALUE, "null argument");
+    if (n_steps < 0) return fail(FAA_ERR_VALUE, "bad step count");
+    if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "multi-step launches support policies of at most 2 ops");
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    faa_rng_t r = *rng;
+    for (int k = 0; k < n_steps; ++k) {
+        if (int e = augment_common(p, d_in[k], batch, 0, d_out[k], batch, h, w, tail, nullptr, nullptr, &r, 0, nullptr,
+                                   1.0f, 0.0f, 1, true, stream)) return e;
+        r.first_index += index_stride;
+    }
+    return FAA_OK;
 }
 
 int faa_augment_tta(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, int replicas, int h, int w,

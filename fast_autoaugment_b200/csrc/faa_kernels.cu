@@ -1295,6 +1295,19 @@ __device__ void build_scalar_stats_table(const AugParams& P, const float* s_norm
 
 // ---------------------------------------------------------------------------------------
 // launch 2
+// self-resolving launches: one image's decisions and program, by one thread (kept out of line: its registers and
+// code must not weigh on the pixel paths)
+static __device__ __noinline__ void self_resolve_prog(const AugParams& P, int i, Prog* dst) {
+    Sample s;
+    Box bx[8];
+    philox_sample(P.sr_rng, P.sr_rng.first_index + (uint64_t)i, P.sr_ops, P.sr_probs, P.sr_n_sub, P.sr_n_op, P.H, P.W,
+                  P.out_h, P.out_w, s, bx);
+    Prog g;
+    build_prog(s, bx, P.sr_ops, P.sr_n_op, P.sr_op_base, P.sr_apply_tail, P.H, P.W, P.out_w, P.sr_allow, g);
+    g.bucket = 0;
+    *dst = g;
+}
+
 template <int OUT, int NSRC, bool TAB>
 static __device__ __forceinline__ void cluster_kernel_body(const AugParams& P) {
     extern __shared__ __align__(128) uint8_t s_dyn[];           // NSRC staged row bands [+ materialisation chunk]
@@ -1312,6 +1325,7 @@ static __device__ __forceinline__ void cluster_kernel_body(const AugParams& P) {
     // Programmatic dependent launch: everything above overlaps the resolve kernel's tail; the
     // schedule and the programs it writes are only read after this point.
     if (!P.chain) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.chain == 3) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // self-resolving, nothing shared between steps
     wait_ticket(P.ready, P.ticket);
 
     // split launches: this (cluster) kernel owns the first n_heavy entries of the schedule
@@ -1331,16 +1345,23 @@ static __device__ __forceinline__ void cluster_kernel_body(const AugParams& P) {
             tma_stage(&s_bar[s], s_dyn + (size_t)s * P.band_cap, P.in + (size_t)src_image(P, src_idx[s]) * img_bytes + s_lo, s_len);
     }
     // per-image programs -> shared memory (24 words each)
+    if (P.self_resolve) {
+        if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < NSRC; ++s)
-        if (threadIdx.x < sizeof(Prog) / 4)
-            reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
-                ld_sched(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x, P.chain);
+            for (int s = 0; s < NSRC; ++s) self_resolve_prog(P, src_idx[s], &st[s].prog);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s)
+            if (threadIdx.x < sizeof(Prog) / 4)
+                reinterpret_cast<uint32_t*>(&st[s].prog)[threadIdx.x] =
+                    ld_sched(reinterpret_cast<const uint32_t*>(P.progs + src_idx[s]) + threadIdx.x, P.chain);
+    }
     __syncthreads();
     // chained steps: the next kernel of the stream may start once every CTA of this one has copied its program
     // (it may overwrite the OTHER program slot only); Sharpness->gather programs also own a scratch image that
     // the next step reuses, so they only release at exit
-    if (P.chain && st[0].prog.cls != C_SG) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (P.chain && P.chain != 3 && st[0].prog.cls != C_SG) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (s_len) {
 #pragma unroll
         for (int s = 0; s < NSRC; ++s) mbar_wait(&s_bar[s], 0);
@@ -2025,7 +2046,12 @@ static cudaError_t launch_one(const AugParams& p, cudaStream_t stream) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.bands, (unsigned)p.B, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    // tiny bands (CIFAR: 1024 pixels per image): fewer threads per CTA = more resident CTAs = more per-CTA latency
+    // chains (program, TMA, first store) in flight
+    static const int small_threads = [] { const char* e = getenv("FAA_SMALL_THREADS"); int v = e ? atoi(e) : 0;
+                                          return (v == 128 || v == 256) ? v : 256; }();      // (make_lut needs 3 warps)
+    const int threads = ((int64_t)p.H * p.W <= (int64_t)p.bands * 2048) ? small_threads : kThreads;
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];

@@ -77,6 +77,12 @@ struct AugParams {
     int32_t grid_y;             // > 0: launch this many schedule rows (CTAs / clusters per band); each one loops over the
                                 // entries row, row + grid_y, ... of its segment.  0: one row per image (B)
     uint32_t* done;             // optional completion counter: every CTA adds 1 when it has finished (release)
+    // self-resolving launches (small batches, cluster kernel only): no resolve kernel, no program array - thread 0 of each
+    // CTA draws its image's decisions (Philox, the same counters as faa_resolve_kernel) and builds the program itself
+    int32_t self_resolve;
+    const OpRec* sr_ops; const double* sr_probs;
+    RngCfg sr_rng;
+    int32_t sr_n_sub, sr_n_op, sr_op_base, sr_apply_tail, sr_allow;
     float scale[3], bias[3];
     float lam, one_minus_lam;   // mixup weights (fp32 of the Python floats)
 };

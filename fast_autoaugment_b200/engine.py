@@ -358,6 +358,35 @@ class FusedAugmenter:
         return out
 
 
+    def plan_many(self, batches, outs):
+        """Pointer tables for :meth:`run_many` (build once, reuse every epoch): validates the tensors like ``__call__``."""
+        if len(batches) != len(outs) or not batches:
+            raise ValueError("need as many outputs as batches (at least one)")
+        b = batches[0].shape[0]
+        for x, o in zip(batches, outs):
+            if (x.dtype != torch.uint8 or not x.is_cuda or not x.is_contiguous() or tuple(x.shape) != (b, self.h, self.w, 3)):
+                raise ValueError("every batch must be a contiguous uint8 CUDA tensor [%d, %d, %d, 3]" % (b, self.h, self.w))
+            if (o.dtype != self.tail.out_dtype or o.device != x.device or x.device != batches[0].device or not o.is_contiguous()
+                    or tuple(o.shape) != (b,) + tuple(self.out_shape[1:])):
+                raise ValueError("every out must be a contiguous %s tensor %s on the batches' device"
+                                 % (self.tail.out_dtype, (b,) + tuple(self.out_shape[1:])))
+        n = len(batches)
+        ins = (C.c_void_p * n)(*[x.data_ptr() for x in batches])
+        dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        return (n, b, ins, dst, batches[0].device, list(batches), list(outs))      # (keeps the tensors alive)
+
+    def run_many(self, plan, first_index: int = 0, stride=None, stream=None):
+        """Augment the planned batches back to back in ONE call (C ABI ``faa_augment_many``): step k == ``self(batches[k],
+        outs[k], first_index + k * stride)``; ``stride`` defaults to the batch size."""
+        n, b, ins, dst, dev = plan[:5]
+        self.rng.first_index = first_index
+        s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            check(lib.faa_augment_many(self.policy.handle, n, ins, dst, b, self.h, self.w, self._t_ref, self._rng_ref,
+                                       int(b if stride is None else stride), C.c_void_p(s)))
+        return plan[6]
+
+
 def augment_tta(policy: CompiledPolicy, batch_u8: torch.Tensor, tail: TailSpec, replicas: int, seed: int, first_index: int = 0,
                 out=None):
     """Test-time-augmentation batching for the policy search (reference search.py:87-125): the reference builds

@@ -161,6 +161,16 @@ int faa_augment_mixup(faa_policy_t* p, const uint8_t* d_in_all, int n_all, int f
                       const faa_rng_t* rng, const int32_t* d_partner, float lam, float one_minus_lam,
                       void* stream);
 
+/* ---- several consecutive batches in one call: the loop `for data, label in loader:` of train.py:47-49 when the
+ * dataset is device-resident (data.py:114-224 replaced by a DeviceDataset) - the caller knows the next n_steps
+ * batches in advance, so their launches are issued back to back without returning to the interpreter (small-image
+ * steps are bound by the host's launch rate otherwise).  Step k reads d_in[k] ([batch][h][w][3] uint8), writes
+ * d_out[k] and draws the decisions of global samples rng->first_index + k*index_stride + i; it equals
+ * faa_augment(..., rng with that first_index, ...).  Policies of at most FAA_MAX_FUSED_OPS ops. */
+int faa_augment_many(faa_policy_t* p, int n_steps, const uint8_t* const* d_in, void* const* d_out,
+                     int batch, int h, int w, const faa_tail_t* tail, const faa_rng_t* rng,
+                     uint64_t index_stride, void* stream);
+
 /* ---- test-time-augmentation batching: replaces the `num_policy` validation loaders of
  * eval_tta (search.py:87-90: one get_dataloaders call per replica, each drawing its own
  * sub-policies for the SAME validation batch, the losses reduced per sample at :116-125).

@@ -208,3 +208,33 @@ def test_lighting_folded_into_the_normalisation_matches_the_reference_chain():
         t = u8[i].permute(2, 0, 1).float().div(255)
         t = t.add(rgb[i].view(3, 1, 1).expand_as(t))
         assert torch.equal(lit[i], (t - m) / sd), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,pol_name", [((32, 32), "fa_reduced_cifar10"), ((224, 224), "fa_resnet50_rimagenet")])
+def test_run_many_and_self_resolving_launches_equal_single_calls(shape, pol_name):
+    """faa_augment_many == a loop of faa_augment; launches too small to split resolve inside the pixel kernel and must
+    equal launches driven by the device sampler's records (the resolve-kernel route) bit for bit"""
+    from fast_autoaugment_b200 import archive
+    from fast_autoaugment_b200.distributed import philox_records
+    from fast_autoaugment_b200.engine import FusedAugmenter
+    H, W = shape
+    B = 96
+    pol = CompiledPolicy(getattr(archive, pol_name)())
+    tail = TailSpec.cifar(16, torch.float16) if H == 32 else TailSpec.imagenet(0, torch.float16)
+    xs = [torch.from_numpy(synth_batch(B, shape, seed=10 + i)).cuda() for i in range(5)]
+    f = FusedAugmenter(pol, tail, H, W, 77)
+    outs = [f.empty_out(B) for _ in range(5)]
+    plan = f.plan_many(xs, outs)
+    f.run_many(plan, 1000, stride=B)
+    torch.cuda.synchronize()
+    many = [o.clone() for o in outs]
+    single = [f(xs[k], f.empty_out(B), 1000 + k * B).clone() for k in range(5)]
+    torch.cuda.synchronize()
+    for a, b in zip(many, single):
+        assert torch.equal(a, b)
+    for k in range(5):
+        d_s, d_b = philox_records(pol, B, H, W, tail, 77, 1000 + k * B, "cuda")
+        samples = d_s.cpu().numpy().reshape(-1).view(_lib.SAMPLE_DTYPE)
+        boxes = d_b.cpu().numpy().reshape(-1).view(_lib.BOX_DTYPE).reshape(B, pol.n_op)
+        assert torch.equal(many[k], augment_batch(pol, xs[k], tail, samples, boxes))
