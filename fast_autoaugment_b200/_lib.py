@@ -64,6 +64,7 @@ def _load():
         "faa_sample_policy_mt": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
         "faa_sample_philox": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, P(Tail), P(Rng), vp, vp, vp]),
         "faa_augment": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), vp, vp, P(Rng), C.c_int, vp]),
+        "faa_policy_set_overlap": (C.c_int, [vp, C.c_int]),
         "faa_augment_many": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), P(Rng), C.c_uint64, vp]),
         "faa_augment_tta": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, P(Tail), P(Rng), vp]),
         "faa_augment_mixup": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, P(Tail),

@@ -212,6 +212,7 @@ struct faa_policy {
     uint64_t last_first_index = 0; bool have_last = false; AheadKey last_key{};
     cudaStream_t ahead_stream = nullptr; cudaEvent_t ev_ahead = nullptr;
     void* d_scratch = nullptr; size_t d_scratch_bytes = 0;   // Sharpness->gather scratch images
+    bool overlap_calls = false;          // faa_policy_set_overlap: consecutive calls on one stream may overlap (see augment_common)
     uint32_t done_target[2] = {0, 0};    // persistent chained steps: CTAs that have been launched on each program slot so far
     int sm_count = 0;
     bool has_sg = false;                 // some sub-policy has Sharpness followed by a geometric op
@@ -669,8 +670,8 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         P.rcp_out_qpr = rcp((uint32_t)(tail->out_w + 3) / 4); P.rcp_w = rcp((uint32_t)w); P.rcp_wq = rcp((uint32_t)w / 4);
         P.rcp_opr = (w & 7) ? 0u : rcp((uint32_t)w / 8);
         static const bool oct_off = [] { const char* e = getenv("FAA_OCTETS"); return e && e[0] == '0'; }();
-        P.octets = (!oct_off && (w & 7) == 0 && tail->out_w == w && tail->out_h == h && tail->out_dtype != FAA_U8_HWC &&
-                    ((uintptr_t)d_out % 16) == 0 && P.stage) ? 1 : 0;
+        P.octets = (!oct_off && (w & 7) == 0 && tail->out_w == w && tail->out_h == h &&
+                    ((uintptr_t)d_out % 16) == 0 && P.stage) ? 1 : 0;          // (uint8 HWC included: 24-byte octets, 8-byte aligned)
     }
     // materialisation chunk: as many rows as fit ~16 KB, at least 3 (single-source launches only)
     {
@@ -697,7 +698,8 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     // (small launches are launch-latency bound: one pixel kernel is faster there)
     size_t split_min = (size_t)4 << 20;                   // pixels per launch from which two pixel kernels pay off
     if (const char* e = getenv("FAA_SPLIT_MIN")) split_min = (size_t)strtoull(e, nullptr, 10);   // tests: force either path
-    const bool use_split = use_order && !split_off && tail->out_dtype != FAA_U8_HWC &&
+    // (uint8 HWC output - the Mixup exchange format - splits when the lean octet paths can write it)
+    const bool use_split = use_order && !split_off && (tail->out_dtype != FAA_U8_HWC || (P.octets && P.crop_pad == 0 && apply_tail)) &&
                            (size_t)batch * h * w >= split_min;
     R.split = use_split ? 1 : 0;
     // Chained steps (default; FAA_CHAIN=0 selects the event schedule): resolve(N+1), [cluster(N),] mid(N), light(N) all on the
@@ -762,6 +764,7 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     const bool no_heavy = use_mid && (R.allow & 6) == 6 && P.mat_cap > 0 && !heavy_always;
     bool use_tab = false;
     if (tail->out_dtype != FAA_U8_HWC) { if (int e = normalisation(p, tail, P, use_tab, stream)) return e; }
+    else { for (int c = 0; c < 3; ++c) { P.scale[c] = 1.0f; P.bias[c] = 0.0f; } }      // lean paths: the byte value itself
     if (p->lighting_rgb && tail->out_dtype != FAA_U8_HWC && apply_tail) {
         // Lighting (augmentations.py:197-215): one normalisation table per image, built on the stream in torch's fp32 order
         if (d_partner) return fail(FAA_ERR_UNSUPPORTED, "Lighting together with fused Mixup is not supported");
@@ -780,17 +783,17 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
     // fused Mixup mixes the fp32 normalised values before the output rounding: the fma shortcut is only proven to round
     // like the exact value for a DIRECT fp16 / bf16 store, so two-source launches always take the exact table
     if (d_partner) use_tab = true;
-    // Self-resolving launch (FAA_SELF=0 turns it off): a launch too small to split is bound by kernel latencies and by the
+    // Self-resolving launch (FAA_SELF=0 turns it off): a launch of tiny images is bound by kernel latencies and by the
     // host's launch rate, not by bytes.  Thread 0 of every CTA draws its image's decisions and builds the program itself
     // (same Philox counters, same build_prog): ONE kernel per step, no program array, no ticket - consecutive steps have
     // no dependency left and overlap through programmatic dependent launch.
     static const bool self_off = [] { const char* e = getenv("FAA_SELF"); return e && e[0] == '0'; }();
-    if (!use_split && !self_off && rng && !d_samples && !d_partner) {
+    if (!use_split && !self_off && rng && !d_samples && !d_partner && (size_t)h * w <= 4096) {     // (tiny images: see below)
         const uintptr_t in0 = (uintptr_t)d_in_all + (in_mod ? 0 : (size_t)first * img_bytes),
                         in1 = in0 + (size_t)(in_mod ? in_mod : batch) * img_bytes;
         const uintptr_t out0 = (uintptr_t)d_out, out1 = out0 + (size_t)batch * tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
         auto overlap = [](uintptr_t a0, uintptr_t a1, const uintptr_t b[2]) { return a0 < b[1] && b[0] < a1; };
-        const bool overlap_ok = p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
+        const bool overlap_ok = p->overlap_calls && p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
                                 !overlap(out0, out1, p->prev_out) && !overlap(out0, out1, p->prev_in) && !P.norm_stride;
         AugParams Ps = P;
         Ps.progs = nullptr; Ps.order = nullptr; Ps.n_heavy = nullptr; Ps.ready = nullptr; Ps.done = nullptr; Ps.grid_y = 0;
@@ -800,12 +803,12 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
         // chain = 1: no griddepcontrol.wait (nothing of the previous kernel is consumed), dependents released once the CTA has
         // its program; a step that touches the previous step's buffers is launched as a plain stream-ordered kernel instead
         Ps.chain = overlap_ok ? 1 : 0; Ps.pdl = 0;
-        // tiny images (CIFAR): Sharpness -> gather programs are evaluated lazily instead of through the scratch image - the
-        // last thing consecutive steps shared - and every CTA releases the next step at once (chain = 3)
-        if ((size_t)h * w <= 4096) {
-            Ps.sr_allow &= ~2; Ps.scratch = nullptr;
-            if (overlap_ok) Ps.chain = 3;
-        }
+        // Only for tiny images (CIFAR): there the one-block resolve kernel is as long as the pixel kernel; for larger images
+        // every band CTA would repeat ~10 us of serial work (measured: 224x224 b2048 uint8 launches 0.90 -> 0.97 ms).
+        // Sharpness -> gather programs are evaluated lazily instead of through the scratch image - the last thing consecutive
+        // steps shared - and every CTA releases the next step at once (chain = 3).
+        Ps.sr_allow &= ~2; Ps.scratch = nullptr;
+        if (overlap_ok) Ps.chain = 3;
         CK(launch_augment(Ps, tail->out_dtype, use_tab, 0, stream));
         g_launches++;
         p->ahead_valid = false;
@@ -841,7 +844,12 @@ static int augment_common(faa_policy_t* p, const uint8_t* d_in_all, int n_all, i
                         in1 = in0 + (size_t)(in_mod ? in_mod : batch) * img_bytes;
         const uintptr_t out0 = (uintptr_t)d_out, out1 = out0 + (size_t)batch * tail->out_h * tail->out_w * 3 * out_elem_size(tail->out_dtype);
         auto overlap = [](uintptr_t a0, uintptr_t a1, const uintptr_t b[2]) { return a0 < b[1] && b[0] < a1; };
-        bool overlap_ok = p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
+        // ... and only if the caller has promised that this call's inputs were complete before the previous call was issued
+        // (faa_policy_set_overlap / faa_augment_many): a kernel launched with programmatic serialization that does not execute
+        // griddepcontrol.wait has no visibility guarantee for what the kernel right in front of it wrote, and that kernel
+        // may be the producer of this batch (a gather, a copy).  Within a call every kernel only consumes what its own
+        // call's first - stream-ordered - kernel already waited for.
+        bool overlap_ok = p->overlap_calls && p->chain_live && p->chain_stream == stream && !overlap(in0, in1, p->prev_out) &&
                           !overlap(out0, out1, p->prev_out) && !overlap(out0, out1, p->prev_in);
         AugParams Pc = P;
         Pc.chain = persist ? 2 : 1; Pc.pdl = 0;
@@ -1031,6 +1039,13 @@ int faa_augment(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, in
                           1.0f, 0.0f, apply_tail, p->n_op <= FAA_MAX_FUSED_OPS, stream);
 }
 
+int faa_policy_set_overlap(faa_policy_t* p, int on) {
+    if (!p) return fail(FAA_ERR_VALUE, "null policy");
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    p->overlap_calls = on != 0;
+    return FAA_OK;
+}
+
 int faa_augment_many(faa_policy_t* p, int n_steps, const uint8_t* const* d_in, void* const* d_out, int batch, int h, int w,
                      const faa_tail_t* tail, const faa_rng_t* rng, uint64_t index_stride, void* stream) {
     if (!p || !rng || !d_in || !d_out) return fail(FAA_ERR_VALUE, "null argument");
@@ -1038,12 +1053,18 @@ int faa_augment_many(faa_policy_t* p, int n_steps, const uint8_t* const* d_in, v
     if (p->n_op > FAA_MAX_FUSED_OPS) return fail(FAA_ERR_UNSUPPORTED, "multi-step launches support policies of at most 2 ops");
     std::lock_guard<std::mutex> call_lk(p->call_mu);
     faa_rng_t r = *rng;
-    for (int k = 0; k < n_steps; ++k) {
-        if (int e = augment_common(p, d_in[k], batch, 0, d_out[k], batch, h, w, tail, nullptr, nullptr, &r, 0, nullptr,
-                                   1.0f, 0.0f, 1, true, stream)) return e;
+    const bool saved = p->overlap_calls;
+    int rc = FAA_OK;
+    for (int k = 0; k < n_steps && rc == FAA_OK; ++k) {
+        // every input exists before this call: steps 2.. may overlap their predecessor; step 1 follows whatever the caller
+        // issued before (stream order) unless the caller made the promise for whole calls too
+        p->overlap_calls = k > 0 ? true : saved;
+        rc = augment_common(p, d_in[k], batch, 0, d_out[k], batch, h, w, tail, nullptr, nullptr, &r, 0, nullptr,
+                            1.0f, 0.0f, 1, true, stream);
         r.first_index += index_stride;
     }
-    return FAA_OK;
+    p->overlap_calls = saved;
+    return rc;
 }
 
 int faa_augment_tta(faa_policy_t* p, const uint8_t* d_in, void* d_out, int batch, int replicas, int h, int w,

@@ -19,8 +19,7 @@
 
 namespace faa {
 
-constexpr float kBias15 = 12582912.0f;           // 1.5 * 2^23: float(kBias15 + i) is exact for |i| < 2^22
-constexpr uint32_t kBias15Bits = 0x4B400000u;
+// (kBias15 = 1.5 * 2^23 and kBias15Bits: faa_kernels.cu, next to the uint8 output helpers)
 
 // byte j (0..3) of w as the float (kBias15 + byte): one PRMT, no conversion instruction
 __device__ __forceinline__ float biased_byte(uint32_t w, int j) {
@@ -32,6 +31,19 @@ __device__ __forceinline__ float biased_byte(uint32_t w, int j) {
 template <int OUT, bool USE_TAB>
 __device__ __forceinline__ void emit_oct_masked(const AugParams& P, const float* tab, typename OutElem<OUT>::T* o,
                                                 uint32_t plane, const uint32_t px[8], uint32_t valid, const float pad[3]) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        uint32_t ob[24];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const uint32_t u = (px[k] >> (8 * ch)) & 255u;
+                const uint32_t b = USE_TAB ? f2b(tab[ch * 256 + u]) : u;
+                ob[3 * k + ch] = ((valid >> k) & 1u) ? b : f2b(pad[ch]);
+            }
+        store_oct_u8(o, ob);
+        return;
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         uint32_t u[8]; float v[8];
@@ -46,6 +58,13 @@ __device__ __forceinline__ void emit_oct_masked(const AugParams& P, const float*
 
 template <int OUT>
 __device__ __forceinline__ void fill_oct(typename OutElem<OUT>::T* o, uint32_t plane, const float pad[3]) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        uint32_t ob[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) ob[k] = f2b(pad[k % 3]);
+        store_oct_u8(o, ob);
+        return;
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float v[8] = {pad[ch], pad[ch], pad[ch], pad[ch], pad[ch], pad[ch], pad[ch], pad[ch]};
@@ -84,7 +103,8 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
     const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
     const uint32_t plane = (uint32_t)H * (uint32_t)W, pitch = (uint32_t)W * 3u;
     const uint32_t s_len = c.s_len2 ? c.s_len2 + 2u : 0u;
-    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    constexpr uint32_t PS = PixStep<OUT>::v;
+    T* dst = reinterpret_cast<T*>(out_img) + PS * (uint32_t)oy0 * (uint32_t)W;
     FastDiv dq; dq.init(opr, P.rcp_opr);
     uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
     const uint32_t dr = dq.div(blockDim.x), dxo = blockDim.x - dr * opr;
@@ -95,7 +115,7 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
         const int s0 = rs.shear ? (rs.a2 + rs.a1 * y) >> 16 : rs.dx + (ax0 >= rs.bx);
         const int s7 = rs.shear ? s0 : rs.dx + (ax0 + 7 >= rs.bx);
         const int sx0 = ax0 + s0;
-        T* o = dst + 8u * i;
+        T* o = dst + PS * 8u * i;
         if ((unsigned)ys >= (unsigned)H || sx0 + 7 + (s7 - s0) < 0 || sx0 >= W) {
             fill_oct<OUT>(o, plane, pad);                                 // nothing of the octet has a source
         } else if (s0 == s7) {
@@ -123,6 +143,19 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
 #pragma unroll
             for (int j = 0; j < 6; ++j) w[j] = __funnelshift_r(v[j], v[j + 1], 8u * k);
             const bool patch = __any_sync(__activemask(), vmask != 0xFFu);
+            if constexpr (OUT == OUT_U8_HWC) {
+                uint32_t ob[24];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)                           // output pixel kk = source pixel (FLIP ? 7 - kk : kk)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const int bi = 3 * (FLIP ? 7 - kk : kk) + ch;
+                        const uint32_t u = (w[bi >> 2] >> (8 * (bi & 3))) & 255u;
+                        const uint32_t b = USE_TAB ? f2b(tab[ch * 256 + u]) : u;
+                        ob[3 * kk + ch] = ((vmask >> kk) & 1u) ? b : f2b(pad[ch]);
+                    }
+                store_oct_u8(o, ob);
+            } else {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 uint32_t u[8]; float nv[8];
@@ -140,6 +173,7 @@ __device__ __forceinline__ void final_rows_rowshift(const AugParams& P, const fl
                     for (int kk = 0; kk < 8; ++kk) nv[kk] = ((vmask >> kk) & 1u) ? nv[kk] : pad[ch];
                 }
                 store_plane8<OUT>(o + ch * plane, nv);
+            }
             }
         } else {
             // a shift break (Pillow's accumulated float offset) inside the octet: per pixel
@@ -202,7 +236,8 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
     const int W = P.W, H = P.H;
     const uint32_t npx = (uint32_t)(oy1 - oy0) * (uint32_t)W;
     const uint32_t plane = (uint32_t)H * (uint32_t)W;
-    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    constexpr uint32_t PS = PixStep<OUT>::v;
+    T* dst = reinterpret_cast<T*>(out_img) + PS * (uint32_t)oy0 * (uint32_t)W;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     uint32_t* my = tile + warp * 128u;
     const uint8_t* raw = c.raw;
@@ -240,7 +275,19 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
             const uint4 q4 = reinterpret_cast<const uint4*>(my)[lane];
             const uint32_t px[4] = {q4.x, q4.y, q4.z, q4.w};
             const bool patch = __any_sync(__activemask(), ((q4.x & q4.y & q4.z & q4.w) >> 24) == 0u);
-            T* o = dst + p0;
+            T* o = dst + PS * p0;
+            if constexpr (OUT == OUT_U8_HWC) {
+                uint32_t ob[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const uint32_t u = (px[k] >> (8 * ch)) & 255u;
+                        const uint32_t b = USE_TAB ? f2b(tab[ch * 256 + u]) : u;
+                        ob[3 * k + ch] = (px[k] >> 24) ? b : f2b(pad[ch]);
+                    }
+                store_quad_u8(o, ob);
+            } else {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float v[4];
@@ -258,6 +305,7 @@ __device__ __forceinline__ void final_rows_gather_t(const AugParams& P, const fl
                     for (int k = 0; k < 4; ++k) v[k] = (px[k] >> 24) ? v[k] : pad[ch];
                 }
                 store_plane4<OUT>(o + ch * plane, v, true, 4);
+            }
             }
         }
         __syncwarp();
@@ -329,7 +377,8 @@ __device__ __forceinline__ void final_rows_color(const AugParams& P, const float
     const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
     const uint32_t plane = (uint32_t)P.H * (uint32_t)W;
     const uint8_t* src = c.sraw + ((uint32_t)oy0 * (uint32_t)W * 3u - c.s_lo);
-    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    constexpr uint32_t PS = PixStep<OUT>::v;
+    T* dst = reinterpret_cast<T*>(out_img) + PS * (uint32_t)oy0 * (uint32_t)W;
     FastDiv dq; dq.init(opr, P.rcp_opr);
     uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
     const uint32_t dr = dq.div(blockDim.x), dxo = blockDim.x - dr * opr;
@@ -361,7 +410,15 @@ __device__ __forceinline__ void final_rows_color(const AugParams& P, const float
                 v[ch][k] = __fadd_rn(z, -kBias15);                       // the byte value as a float, exact
             }
         }
-        T* o = dst + 8u * i;
+        T* o = dst + PS * 8u * i;
+        if constexpr (OUT == OUT_U8_HWC) {
+            uint32_t ob[24];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) ob[3 * k + ch] = f2b(v[ch][k]);
+            store_oct_u8(o, ob);
+        } else {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             float nv[8];
@@ -377,6 +434,7 @@ __device__ __forceinline__ void final_rows_color(const AugParams& P, const float
                 }
             }
             store_plane8<OUT>(o + ch * plane, nv);
+        }
         }
         ox += dxo; r += dr;
         if (ox >= opr) { ox -= opr; ++r; }
@@ -394,7 +452,8 @@ __device__ __forceinline__ void final_rows_cutout(const AugParams& P, const floa
     const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
     const uint32_t plane = (uint32_t)P.H * (uint32_t)W;
     const uint8_t* src = c.sraw + ((uint32_t)oy0 * (uint32_t)W * 3u - c.s_lo);
-    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    constexpr uint32_t PS = PixStep<OUT>::v;
+    T* dst = reinterpret_cast<T*>(out_img) + PS * (uint32_t)oy0 * (uint32_t)W;
     FastDiv dq; dq.init(opr, P.rcp_opr);
     uint32_t r = dq.div(threadIdx.x), ox = threadIdx.x - r * opr;
     const uint32_t dr = dq.div(blockDim.x), dxo = blockDim.x - dr * opr;
@@ -405,7 +464,7 @@ __device__ __forceinline__ void final_rows_cutout(const AugParams& P, const floa
         const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * (r * opr + sox));
         const uint2 wa = s8[0], wb = s8[1], wc = s8[2];
         const uint32_t w[6] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y};
-        T* o = dst + 8u * i;
+        T* o = dst + PS * 8u * i;
         if (y < bx.y0 || y > bx.y1 || sx0 + 7 < bx.x0 || sx0 > bx.x1) {
             if (flip) stream_oct<OUT, TAB, true>(P, w, s_norm, o, plane);
             else stream_oct<OUT, TAB, false>(P, w, s_norm, o, plane);
@@ -452,6 +511,18 @@ __device__ __forceinline__ void sharp_emit_u8(const float zb[12], uint32_t* w) {
 template <int OUT, bool USE_TAB, bool FLIP>
 __device__ __forceinline__ void sharp_emit(const AugParams& P, const float* tab, const float zb[12], typename OutElem<OUT>::T* o,
                                            uint32_t plane) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        uint32_t ob[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const uint32_t u = __float_as_uint(zb[3 * (FLIP ? 3 - k : k) + ch]) & 255u;
+                ob[3 * k + ch] = USE_TAB ? f2b(tab[ch * 256 + u]) : u;
+            }
+        store_quad_u8(o, ob);
+        return;
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         float v[4];
@@ -479,7 +550,8 @@ __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const floa
     const uint32_t qpr = (uint32_t)W >> 2;
     const uint32_t nq = (uint32_t)(oy1 - oy0) * qpr;
     const uint32_t plane = (uint32_t)H * (uint32_t)W, pitch = (uint32_t)W * 3u;
-    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)W;
+    constexpr uint32_t PS = PixStep<OUT>::v;
+    T* dst = reinterpret_cast<T*>(out_img) + PS * (uint32_t)oy0 * (uint32_t)W;
     FastDiv dq; dq.init(qpr, P.rcp_wq);
     uint32_t r = dq.div(threadIdx.x), qx = threadIdx.x - r * qpr;
     const uint32_t dr = dq.div(blockDim.x), dxq = blockDim.x - dr * qpr;
@@ -551,7 +623,7 @@ __device__ __forceinline__ void final_rows_sharp4(const AugParams& P, const floa
         if (u8_dst != nullptr) {
             sharp_emit_u8(zb, reinterpret_cast<uint32_t*>(u8_dst + (uint32_t)y * pitch + 12u * sqx));
         } else {
-            T* o = dst + 4u * q;
+            T* o = dst + PS * 4u * q;
             if (flip) sharp_emit<OUT, USE_TAB, true>(P, tab, zb, o, plane);
             else sharp_emit<OUT, USE_TAB, false>(P, tab, zb, o, plane);
         }

@@ -645,10 +645,34 @@ __device__ __forceinline__ void quad_generic(const Ctx& c, const TailInfo& t, in
 template <int OUT> struct OutElem { using T = float; };
 template <> struct OutElem<OUT_F16> { using T = __half; };
 template <> struct OutElem<OUT_BF16> { using T = __nv_bfloat16; };
+template <> struct OutElem<OUT_U8_HWC> { using T = uint8_t; };
+
+// ---- output addressing of the lean paths.  Planar float outputs step ONE element per pixel and `plane` elements per
+// channel; the uint8 HWC output (Mixup exchange, PIL surface) steps three bytes per pixel.  With OUT_U8_HWC the values the
+// paths produce are the augmented BYTES (identity "normalisation": scale 1, bias 0; float tables hold byte values).
+template <int OUT> struct PixStep { static constexpr uint32_t v = OUT == OUT_U8_HWC ? 3u : 1u; };
+constexpr float kBias15 = 12582912.0f;           // 1.5 * 2^23: float(kBias15 + i) is exact for |i| < 2^22
+constexpr uint32_t kBias15Bits = 0x4B400000u;
+// a float holding an integer 0..255 -> that integer (no F2I: the conversion unit is 1/8 rate)
+__device__ __forceinline__ uint32_t f2b(float v) { return __float_as_uint(__fadd_rn(v, kBias15)) & 255u; }
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) { return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24); }
+// 24 bytes = 8 pixels in output order (8-byte aligned: W % 8 == 0) / 12 bytes = 4 pixels (4-byte aligned)
+__device__ __forceinline__ void store_oct_u8(uint8_t* o, const uint32_t b[24]) {
+    uint2* q = reinterpret_cast<uint2*>(o);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) q[j] = make_uint2(pack4(b[8 * j], b[8 * j + 1], b[8 * j + 2], b[8 * j + 3]), pack4(b[8 * j + 4], b[8 * j + 5], b[8 * j + 6], b[8 * j + 7]));
+}
+__device__ __forceinline__ void store_quad_u8(uint8_t* o, const uint32_t b[12]) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) q[j] = pack4(b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]);
+}
 
 template <int OUT>
 __device__ __forceinline__ void store_plane4(typename OutElem<OUT>::T* o, const float v[4], bool vec, int nvalid) {
-    if (vec) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        (void)o; (void)v; (void)vec; (void)nvalid;                   // (uint8 HWC goes through store_quad_u8 / emit_quad)
+    } else if (vec) {
         if constexpr (OUT == OUT_F32) {
             *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         } else if constexpr (OUT == OUT_F16) {
@@ -778,6 +802,23 @@ template <int OUT, bool USE_TAB, bool FLIP>
 __device__ __forceinline__ void stream_quad(const AugParams& P, const uint32_t* w, const float* tab,
                                             typename OutElem<OUT>::T* o, uint32_t plane) {
     const uint32_t w3[3] = {w[0], w[1], w[2]};
+    if constexpr (OUT == OUT_U8_HWC) {
+        if (!USE_TAB && !FLIP) {
+            uint32_t* q = reinterpret_cast<uint32_t*>(o);
+            q[0] = w3[0]; q[1] = w3[1]; q[2] = w3[2];
+        } else {
+            uint32_t ob[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int b = 3 * (FLIP ? 3 - k : k) + ch;
+                    const uint32_t u = (w3[b >> 2] >> (8 * (b & 3))) & 255u;
+                    ob[3 * k + ch] = USE_TAB ? f2b(tab[ch * 256 + u]) : u;
+                }
+            store_quad_u8(o, ob);
+        }
+    } else {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         float v[4];
@@ -788,6 +829,7 @@ __device__ __forceinline__ void stream_quad(const AugParams& P, const uint32_t* 
             v[k] = USE_TAB ? tab[ch * 256 + u] : fmaf((float)u, P.scale[ch], P.bias[ch]);
         }
         store_plane4<OUT>(o + ch * plane, v, true, 4);
+    }
     }
 }
 
@@ -806,11 +848,16 @@ __device__ __forceinline__ void final_rows_stream(const AugParams& P, const floa
     for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
         const int ox0 = (int)qx * 4, oy = oy0 + (int)r;
         const int sx0 = (flip ? (P.out_w - 4 - ox0) : ox0) + t.crop_dx, ay = oy + t.crop_dy;
-        T* o = reinterpret_cast<T*>(out_img) + (uint32_t)(oy * P.out_w + ox0);
+        T* o = reinterpret_cast<T*>(out_img) + PixStep<OUT>::v * (uint32_t)(oy * P.out_w + ox0);
         if ((unsigned)sx0 < (unsigned)c.W && (unsigned)ay < (unsigned)c.H) {
             const uint32_t* w = reinterpret_cast<const uint32_t*>(c.sraw + ((uint32_t)(ay * c.W + sx0) * 3u - c.s_lo));
             if (flip) stream_quad<OUT, USE_TAB, true>(P, w, tab, o, plane);
             else stream_quad<OUT, USE_TAB, false>(P, w, tab, o, plane);
+        } else if constexpr (OUT == OUT_U8_HWC) {
+            uint32_t ob[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ob[k] = f2b(pad[k % 3]);
+            store_quad_u8(o, ob);
         } else {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
@@ -828,7 +875,9 @@ __device__ __forceinline__ void final_rows_stream(const AugParams& P, const floa
 // store (fp16 / bf16) and the normalisation runs as packed fp32x2 fused multiply-adds (sm_100 FFMA2).
 template <int OUT>
 __device__ __forceinline__ void store_plane8(typename OutElem<OUT>::T* o, const float v[8]) {
-    if constexpr (OUT == OUT_F32) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        (void)o; (void)v;                                            // (uint8 HWC goes through store_oct_u8)
+    } else if constexpr (OUT == OUT_F32) {
         reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
         reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else if constexpr (OUT == OUT_F16) {
@@ -866,6 +915,23 @@ __device__ __forceinline__ void norm8(const AugParams& P, const float* tab, int 
 template <int OUT, bool USE_TAB, bool FLIP>
 __device__ __forceinline__ void stream_oct(const AugParams& P, const uint32_t w[6], const float* tab,
                                            typename OutElem<OUT>::T* o, uint32_t plane) {
+    if constexpr (OUT == OUT_U8_HWC) {
+        if (!USE_TAB && !FLIP) {                                     // the bytes themselves
+            uint2* q = reinterpret_cast<uint2*>(o);
+            q[0] = make_uint2(w[0], w[1]); q[1] = make_uint2(w[2], w[3]); q[2] = make_uint2(w[4], w[5]);
+        } else {
+            uint32_t ob[24];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int b = 3 * (FLIP ? 7 - k : k) + ch;
+                    const uint32_t u = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+                    ob[3 * k + ch] = USE_TAB ? f2b(tab[ch * 256 + u]) : u;
+                }
+            store_oct_u8(o, ob);
+        }
+    } else {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         uint32_t u[8]; float v[8];
@@ -877,12 +943,21 @@ __device__ __forceinline__ void stream_oct(const AugParams& P, const uint32_t w[
         norm8<USE_TAB>(P, tab, ch, u, v);
         store_plane8<OUT>(o + ch * plane, v);
     }
+    }
 }
 
 // px[8]: eight 24-bit pixels already in OUTPUT order
 template <int OUT, bool TAB>
 __device__ __forceinline__ void emit_oct(const AugParams& P, const float* s_norm, typename OutElem<OUT>::T* o, uint32_t plane,
                                          const uint32_t px[8]) {
+    if constexpr (OUT == OUT_U8_HWC) {                               // (s_norm is the plain normalisation here: bytes as they are)
+        uint32_t ob[24];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) ob[3 * k + ch] = (px[k] >> (8 * ch)) & 255u;
+        store_oct_u8(o, ob);
+    } else {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         uint32_t u[8]; float v[8];
@@ -890,6 +965,7 @@ __device__ __forceinline__ void emit_oct(const AugParams& P, const float* s_norm
         for (int k = 0; k < 8; ++k) u[k] = (px[k] >> (8 * ch)) & 255u;
         norm8<TAB>(P, s_norm, ch, u, v);
         store_plane8<OUT>(o + ch * plane, v);
+    }
     }
 }
 
@@ -906,13 +982,14 @@ __device__ __forceinline__ void final_rows_stream8(const AugParams& P, const flo
     const uint32_t n8 = (uint32_t)(oy1 - oy0) * opr;
     const uint32_t plane = (uint32_t)P.H * (uint32_t)P.W;
     const uint8_t* src = c.sraw + ((uint32_t)oy0 * (uint32_t)P.W * 3u - c.s_lo);   // first byte of row oy0 (staged)
-    T* dst = reinterpret_cast<T*>(out_img) + (uint32_t)oy0 * (uint32_t)P.W;
+    constexpr uint32_t PS = PixStep<OUT>::v;
+    T* dst = reinterpret_cast<T*>(out_img) + PS * (uint32_t)oy0 * (uint32_t)P.W;
     if (!FLIP) {                                                  // source and output both advance linearly
         for (uint32_t i = threadIdx.x; i < n8; i += blockDim.x) {
             const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * i);
             const uint2 a = s8[0], b = s8[1], d = s8[2];
             const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
-            stream_oct<OUT, USE_TAB, false>(P, w, tab, dst + 8u * i, plane);
+            stream_oct<OUT, USE_TAB, false>(P, w, tab, dst + PS * 8u * i, plane);
         }
     } else {
         FastDiv dq; dq.init(opr, P.rcp_opr);
@@ -922,7 +999,7 @@ __device__ __forceinline__ void final_rows_stream8(const AugParams& P, const flo
             const uint2* s8 = reinterpret_cast<const uint2*>(src + 24u * (r * opr + (opr - 1u - ox)));
             const uint2 a = s8[0], b = s8[1], d = s8[2];
             const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
-            stream_oct<OUT, USE_TAB, true>(P, w, tab, dst + 8u * i, plane);
+            stream_oct<OUT, USE_TAB, true>(P, w, tab, dst + PS * 8u * i, plane);
             ox += dx; r += dr;
             if (ox >= opr) { ox -= opr; ++r; }
         }
@@ -934,8 +1011,8 @@ __device__ __forceinline__ void final_rows_stream8(const AugParams& P, const flo
 template <int OUT, bool TAB, bool LUT, bool OCT = false>
 __device__ __forceinline__ void final_rows_plain_lut(const AugParams& P, const float* s_norm, const float* ftab, const Ctx& c,
                                                      const uint8_t* lutc, const TailInfo& t, void* out_img, int oy0, int oy1) {
-    if constexpr (OUT != OUT_U8_HWC) {
-        if ((!LUT || ftab != nullptr) && band_fully_staged(c, t, oy0, oy1)) {
+    if constexpr (OUT != OUT_U8_HWC || OCT) {                       // (uint8 HWC: only the octet paths of the light kernel)
+        if ((!LUT || ftab != nullptr) && band_fully_staged(c, t, oy0, oy1) && (OUT != OUT_U8_HWC || (OCT && octet_geometry(P, t)))) {
             if (OCT && octet_geometry(P, t)) {                 // (the light kernel: 8 pixels per thread and iteration)
                 if (t.flip) {
                     if (LUT) final_rows_stream8<OUT, true, true>(P, ftab, c, out_img, oy0, oy1);
@@ -1497,7 +1574,7 @@ __global__ void __launch_bounds__(kMidThreadsMax, 2) faa_augment_mid_kernel(cons
 
     const int y0 = P.geo[0].y[band], y1 = P.geo[0].y[band + 1];
     const int oy0 = P.geo[0].oy[band], oy1 = P.geo[0].oy[band + 1];
-    const size_t out_elem = OUT == OUT_F32 ? 4 : 2;
+    const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
     const int cls = st.prog.cls;
     const Ctx c = make_ctx(P, P.in + (size_t)src_image(P, idx) * img_bytes, s_dyn, s_lo, s_len, P.H, P.W, st, true);
@@ -1647,8 +1724,8 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     __shared__ Prog s_prog;
     __shared__ __align__(16) uint8_t s_lut[2][768];
     __shared__ __align__(16) uint8_t s_lutc[768];
-    __shared__ float s_ftab[OUT == OUT_U8_HWC ? 1 : 768];       // LUT programs: normalise(ch, lutc[ch][b])
-    __shared__ __align__(16) uint32_t s_tile[OUT == OUT_U8_HWC ? 4 : (kThreads / 32) * 128];   // affine gather tiles (128 px per warp)
+    __shared__ float s_ftab[768];                                // LUT programs: normalise(ch, lutc[ch][b])
+    __shared__ __align__(16) uint32_t s_tile[(kThreads / 32) * 128];   // affine gather tiles (128 px per warp)
     __shared__ float s_norm[TAB ? 768 : 1];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -1690,7 +1767,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
                 if (lut_mask & 1u) v = s_lut[0][base + v];
                 if (lut_mask & 2u) v = s_lut[1][base + v];
                 s_lutc[i] = (uint8_t)v;
-                if constexpr (OUT != OUT_U8_HWC) s_ftab[i] = normalise<TAB>(P, s_norm, i >> 8, v);
+                s_ftab[i] = normalise<TAB>(P, s_norm, i >> 8, v);      // (uint8 HWC output: scale 1, bias 0 - the byte as a float)
             }
             __syncthreads();
         }
@@ -1710,7 +1787,7 @@ __global__ void __launch_bounds__(kThreads, FAA_LIGHT_CTAS) faa_augment_light_ke
     const size_t out_elem = OUT == OUT_F32 ? 4 : (OUT == OUT_U8_HWC ? 1 : 2);
     void* out_img = reinterpret_cast<uint8_t*>(P.out) + (size_t)img * 3u * (size_t)P.out_h * (size_t)P.out_w * out_elem;
     bool done = false;
-    if constexpr (OUT != OUT_U8_HWC) {
+    {
         // lean octet paths (faa_fast.cuh) for the common geometry; everything else takes the generic evaluators
         // (C_GEOM2 only exists in launches whose geometry the lean gather handles: build_prog, allow bit 2)
         if (cls == C_GEOM2 || ((cls == C_GEOM || cls == C_POINT) && octet_geometry(P, t) && band_fully_staged(c, t, oy0, oy1))) {
@@ -2096,9 +2173,7 @@ static cudaError_t launch_light(const AugParams& p, cudaStream_t stream) {
 
 template <int OUT, bool TAB>
 static cudaError_t launch_mid(const AugParams& p, cudaStream_t stream) {
-    if constexpr (OUT == OUT_U8_HWC) {
-        return cudaErrorInvalidValue;                            // the mid kernel writes float planes only
-    } else {
+    {
         const size_t dyn = (size_t)p.geo[0].band_cap;
         static size_t configured[kMaxDevices] = {};
         int dev = 0;

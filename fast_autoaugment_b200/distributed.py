@@ -168,6 +168,8 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
     oh, ow = tail.out_size if tail.out_size is not None else (h, w)
     n_recv = sum(recv_counts)
     pool = torch.empty((b + n_recv, oh, ow, 3), dtype=torch.uint8, device=dev)      # [own augmented shard | received partners]
+    if timing is not None:
+        timing["a0"] = torch.cuda.Event(enable_timing=True); timing["a0"].record()
     aug = augment_batch(policy, local_u8, u8_tail, rng=rng, out=pool[:b])
     # 2. partners: straight into the tail of the pool
     if timing is not None:
@@ -187,7 +189,11 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
         ids = torch.cat([torch.arange(lo, lo + b, dtype=torch.int64), recv_global]).to(dev)
         zp = zb_all.index_select(0, ids)
         za = zp[:b]
+    if timing is not None:
+        timing["m0"] = torch.cuda.Event(enable_timing=True); timing["m0"].record()
     data = mix_augmented(policy, aug, pool, partner_pool, tail, lam, za, zp)
+    if timing is not None:
+        timing["m1"] = torch.cuda.Event(enable_timing=True); timing["m1"].record()
     return data, targets, all_targets[perm[lo:lo + b].to(all_targets.device)], lam
 
 

@@ -323,9 +323,14 @@ class FusedAugmenter:
         aug(batch_u8_cuda, out_cuda, first_index)     # asynchronous on the current stream
     """
 
-    def __init__(self, policy: CompiledPolicy, tail: TailSpec, h: int, w: int, seed: int = 0):
+    def __init__(self, policy: CompiledPolicy, tail: TailSpec, h: int, w: int, seed: int = 0, overlap_calls: bool = False):
+        """``overlap_calls=True``: consecutive ``__call__``s on one stream may overlap on the GPU (C ABI
+        ``faa_policy_set_overlap``) - only if every call's input batch was complete before the PREVIOUS call was issued
+        (device-resident data, a producer that runs a batch ahead).  ``run_many`` overlaps its steps regardless."""
         if policy.n_op > _lib.MAX_FUSED_OPS:
             raise ValueError("FusedAugmenter handles policies of at most 2 ops; use augment_batch")
+        if overlap_calls:
+            check(lib.faa_policy_set_overlap(policy.handle, 1))
         self.policy, self.tail, self.h, self.w = policy, tail, h, w
         self.t = tail.c_struct(h, w)
         self.rng = make_rng(seed, 0, tail)

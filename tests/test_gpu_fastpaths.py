@@ -86,6 +86,10 @@ def test_octet_paths_match_oracle(shape, norm, split_min, monkeypatch):
         got = augment_batch(pol, x, tail, samples, boxes).cpu()
         bad = [(i, policies[i]) for i in range(n) if not torch.equal(got[i], want[i].to(dt))]
         assert not bad, (shape, dt, split_min, len(bad), bad[:6])
+    # uint8 HWC output (the Mixup exchange format) through the same lean paths: the augmented bytes themselves
+    got = augment_batch(pol, x, TailSpec(None, 0, True, mean, std, 0, torch.uint8), samples, boxes).cpu().numpy()
+    bad = [(i, policies[i]) for i in range(n) if not np.array_equal(got[i], want_u8[i])]
+    assert not bad, (shape, "uint8", split_min, len(bad), bad[:6])
     # CutoutDefault post-pass on top of the octet paths
     tail = TailSpec(None, 0, True, mean, std, 16, torch.float32)
     for i in range(n):

@@ -11,7 +11,7 @@ B = int(os.environ.get("CIFAR_B", "512"))
 x = [torch.from_numpy(bench.synth_batch(B, 32, 32, 1 + i)).cuda() for i in range(4)]
 pol = CompiledPolicy(archive.fa_reduced_cifar10())
 tail = TailSpec.cifar(16, torch.float16)
-f = FusedAugmenter(pol, tail, 32, 32, 1)
+f = FusedAugmenter(pol, tail, 32, 32, 1, overlap_calls=True)
 outs = [f.empty_out(B) for _ in range(4)]
 for i in range(20): f(x[i % 4], outs[i % 4], i * B)
 torch.cuda.synchronize()

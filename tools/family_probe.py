@@ -27,7 +27,7 @@ for kind, fam in enumerate(("noise", "ramp", "constant")):
     x = [batch(kind, 10 + i) for i in range(4)]
     for name in ("Invert", "AutoContrast", "Equalize", "Contrast", "Sharpness", "Rotate"):
         pol = CompiledPolicy([[(name, 1.0, 0.7), (name, 0.0, 0.7)]])
-        f = FusedAugmenter(pol, tail, H, W, 1)
+        f = FusedAugmenter(pol, tail, H, W, 1, overlap_calls=True)
         outs = [f.empty_out(B) for _ in range(4)]
         for i in range(5):
             f(x[i % 4], outs[i % 4], i * B)

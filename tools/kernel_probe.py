@@ -20,7 +20,7 @@ x = [torch.from_numpy(bench.synth_batch(B, H, W, 1 + i)).cuda() for i in range(4
 
 def timeit(name, policies, tail, n=int(os.environ.get("PROBE_N", "200"))):
     pol = CompiledPolicy(policies)
-    f = FusedAugmenter(pol, tail, H, W, 1)
+    f = FusedAugmenter(pol, tail, H, W, 1, overlap_calls=True)
     outs = [f.empty_out(B) for _ in range(4)]
     for i in range(5):
         f(x[i % 4], outs[i % 4], i * B)

@@ -11,7 +11,7 @@ H, W, B = 224, 224, 512
 x = [torch.from_numpy(bench.synth_batch(B, H, W, 1 + i)).cuda() for i in range(4)]
 pol = CompiledPolicy(archive.fa_resnet50_rimagenet())
 tail = TailSpec.imagenet(0, torch.float16)
-f = FusedAugmenter(pol, tail, H, W, 1)
+f = FusedAugmenter(pol, tail, H, W, 1, overlap_calls=True)
 outs = [f.empty_out(B) for _ in range(4)]
 for i in range(5): f(x[i % 4], outs[i % 4], i * B)
 torch.cuda.synchronize()

@@ -23,7 +23,7 @@ for name, pol_list in CASES:
     if want and name not in want:
         continue
     pol = CompiledPolicy(pol_list)
-    f = FusedAugmenter(pol, tail, H, W, 1)
+    f = FusedAugmenter(pol, tail, H, W, 1, overlap_calls=True)
     outs = [f.empty_out(B) for _ in range(2)]
     f(x[0], outs[0], 0); f(x[1], outs[1], B)
     torch.cuda.synchronize()

@@ -14,7 +14,7 @@ pairs = [("Brightness", "Sharpness"), ("Contrast", "Sharpness"), ("Rotate", "Sha
          ("AutoContrast", "Rotate"), ("Contrast", "Cutout"), ("Equalize", "AutoContrast"), ("Posterize", "Equalize")]
 for a, b in pairs:
     pol = CompiledPolicy([[(a, 1.0, 0.7), (b, 1.0, 0.6)]])
-    f = FusedAugmenter(pol, tail, H, W, 1)
+    f = FusedAugmenter(pol, tail, H, W, 1, overlap_calls=True)
     outs = [f.empty_out(B) for _ in range(4)]
     for i in range(5): f(x[i % 4], outs[i % 4], i * B)
     torch.cuda.synchronize()

@@ -40,7 +40,7 @@ tail = TailSpec.imagenet(0, torch.float16)
 x = torch.from_numpy(synth_batch(96, (224, 224), seed=2)).cuda()
 for chain in ("0", "1"):
     os.environ["FAA_CHAIN"] = chain
-    f = FusedAugmenter(p2, tail, 224, 224, 5)
+    f = FusedAugmenter(p2, tail, 224, 224, 5, overlap_calls=True)
     outs = [f(x, f.empty_out(96), i * 96) for i in range(4)]
     torch.cuda.synchronize()
 os.environ["FAA_CHAIN"] = "0"
