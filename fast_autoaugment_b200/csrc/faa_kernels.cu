@@ -2000,9 +2000,15 @@ struct MixU8Params {
 
 template <typename T>
 __global__ void __launch_bounds__(256) faa_mix_u8_kernel(const __grid_constant__ MixU8Params P) {
-    __shared__ float s_tab[768];
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_tab[i] = __ldg(P.norm_tab + i);
+    // both products of aug_mixup.py:21 as tables: round(norm(b) * lam), round(norm(b) * (1 - lam)) - the same two roundings
+    // as the reference's tensor ops, then ONE add per value in the loop
+    __shared__ float s_la[768], s_ob[768];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const float t = __ldg(P.norm_tab + i);
+        s_la[i] = f_mul(t, P.lam); s_ob[i] = f_mul(t, P.oml);
+    }
     __syncthreads();
+    const float za_val = f_mul(0.0f, P.lam), zb_val = f_mul(0.0f, P.oml);     // a zeroed (CutoutDefault) value, scaled
     const int img = blockIdx.y, pi = __ldg(P.partner + img);
     const uint32_t npx = (uint32_t)P.H * (uint32_t)P.W, nq = npx >> 2;
     const uint32_t* a = reinterpret_cast<const uint32_t*>(P.a + (size_t)img * npx * 3u);
@@ -2029,11 +2035,17 @@ __global__ void __launch_bounds__(256) faa_mix_u8_kernel(const __grid_constant__
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             float v[4];
+            if (ma | mb) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float fa = ((ma >> k) & 1u) ? 0.0f : s_tab[ch * 256 + ((pa[k] >> (8 * ch)) & 255u)];
-                const float fb = ((mb >> k) & 1u) ? 0.0f : s_tab[ch * 256 + ((pb[k] >> (8 * ch)) & 255u)];
-                v[k] = f_add(f_mul(fa, P.lam), f_mul(fb, P.oml));                 // aug_mixup.py:21
+                for (int k = 0; k < 4; ++k) {
+                    const float fa = ((ma >> k) & 1u) ? za_val : s_la[ch * 256 + ((pa[k] >> (8 * ch)) & 255u)];
+                    const float fb = ((mb >> k) & 1u) ? zb_val : s_ob[ch * 256 + ((pb[k] >> (8 * ch)) & 255u)];
+                    v[k] = f_add(fa, fb);                                         // aug_mixup.py:21
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    v[k] = f_add(s_la[ch * 256 + ((pa[k] >> (8 * ch)) & 255u)], s_ob[ch * 256 + ((pb[k] >> (8 * ch)) & 255u)]);
             }
             T* op = o + (size_t)ch * npx + 4u * q;
             if constexpr (sizeof(T) == 4) {

@@ -43,11 +43,43 @@ def global_pairing(global_batch: int, alpha: float, seed: int, step: int):
     g = torch.Generator(device="cpu")
     g.manual_seed((int(seed) * 1000003 + int(step)) & 0x7FFFFFFFFFFFFFFF)
     perm = torch.randperm(global_batch, generator=g)
-    rs = np.random.RandomState((int(seed) * 7919 + int(step)) & 0xFFFFFFFF)
+    # (a counter-seeded generator: 8 us to construct; RandomState(seed) costs 100 us of Mersenne-Twister seeding per step)
+    rs = np.random.Generator(np.random.PCG64([int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFFFFFFFFFF]))
     lam = rs.beta(alpha, alpha)
     lam = max(lam, 1.0 - lam)
     assert 0.0 <= lam <= 1.0, lam
     return perm, float(lam)
+
+
+class _PinnedRing:
+    """Small CPU index tensors go to the device through pinned staging buffers and ``non_blocking`` copies: a plain
+    ``.to(device)`` of pageable memory blocks the host until everything queued on the stream has run, which serialises the
+    host's planning of step N+1 with the kernels of step N.  A buffer is reused only after the copy that read it has run."""
+    _rings = {}
+
+    @classmethod
+    def upload(cls, t: torch.Tensor, device, dtype=None) -> torch.Tensor:
+        t = t.contiguous() if dtype is None else t.to(dtype).contiguous()
+        n = t.numel()
+        out = torch.empty(t.shape, dtype=t.dtype, device=device)
+        if n == 0:
+            return out
+        key = (str(device), t.dtype, 1 << max(6, (n - 1).bit_length()))
+        ring = cls._rings.setdefault(key, {"bufs": [], "evs": [], "next": 0})
+        if len(ring["bufs"]) < 8:
+            ring["bufs"].append(torch.empty(key[2], dtype=t.dtype).pin_memory())
+            ring["evs"].append(None)
+            i = len(ring["bufs"]) - 1
+        else:
+            i = ring["next"]; ring["next"] = (i + 1) % 8
+            if ring["evs"][i] is not None:
+                ring["evs"][i].synchronize()
+        buf = ring["bufs"][i][:n]
+        buf.copy_(t.reshape(-1))
+        out.reshape(-1).copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(device))
+        ring["evs"][i] = ev
+        return out
 
 
 def gather_pool(local: torch.Tensor, group=None) -> torch.Tensor:
@@ -76,6 +108,9 @@ def partner_plan(perm: torch.Tensor, rank: int, world: int):
     n = int(perm.numel())
     b = n // world
     perm = perm.to(torch.int64).cpu()
+    if world == 1:                                              # every partner is local: nothing is sent
+        e = torch.empty(0, dtype=torch.int64)
+        return e, [0], [0], perm.clone(), e
     owner = perm // b                                           # rank that owns each sample's partner
     lo = rank * b
     send_idx, send_counts = [], []
@@ -131,7 +166,8 @@ def mix_augmented(policy: CompiledPolicy, a_u8: torch.Tensor, pool_u8: torch.Ten
     t = tail.c_struct(h, w)
     if out is None:
         out = torch.empty((b, 3, h, w), dtype=tail.out_dtype, device=a_u8.device)
-    part = partner_pool.to(device=a_u8.device, dtype=torch.int32).contiguous()
+    part = partner_pool if (partner_pool.is_cuda and partner_pool.dtype == torch.int32) else \
+        _PinnedRing.upload(partner_pool.cpu(), a_u8.device, torch.int32)
     za = zero_box_a.contiguous() if zero_box_a is not None else None
     zp = zero_box_pool.contiguous() if zero_box_pool is not None else None
     with torch.cuda.device(a_u8.device):
@@ -161,6 +197,10 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
     perm, lam = global_pairing(n, alpha, seed, step)
     lo, _ = shard_bounds(n, rank, world)
     send_idx, send_counts, recv_counts, partner_pool, recv_global = partner_plan(perm, rank, world)
+    # the plan goes to the device BEFORE any kernel of this step is queued (asynchronous copies from pinned staging)
+    partner_dev = _PinnedRing.upload(partner_pool, dev, torch.int32)
+    send_dev = _PinnedRing.upload(send_idx, dev) if world > 1 else None
+    tgt_idx_dev = _PinnedRing.upload(perm[lo:lo + b], dev)
     # 1. this shard, augmented to uint8 (the CutoutDefault box acts on the normalised tensor: step 3)
     u8_tail = TailSpec(tail.out_size, tail.crop_pad, tail.hflip, tail.mean, tail.std, 0, torch.uint8)
     rng = make_rng(seed, step * n + lo, tail)
@@ -175,7 +215,7 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
     if timing is not None:
         timing["ex0"] = torch.cuda.Event(enable_timing=True); timing["ex0"].record()
     if world > 1:
-        send = aug.index_select(0, send_idx.to(dev))
+        send = aug.index_select(0, send_dev)
         dist.all_to_all_single(pool[b:], send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=group)
     all_targets = gather_pool(targets, group) if world > 1 else targets
     if timing is not None:
@@ -186,15 +226,15 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
     if tail.cutout > 0:
         rec_s, _ = philox_records(policy, n, h, w, tail, seed, step * n, dev)
         zb_all = rec_s[:, 8:16].contiguous().view(torch.int16)                      # faa_sample_t.zero_box
-        ids = torch.cat([torch.arange(lo, lo + b, dtype=torch.int64), recv_global]).to(dev)
+        ids = _PinnedRing.upload(torch.cat([torch.arange(lo, lo + b, dtype=torch.int64), recv_global]), dev)
         zp = zb_all.index_select(0, ids)
         za = zp[:b]
     if timing is not None:
         timing["m0"] = torch.cuda.Event(enable_timing=True); timing["m0"].record()
-    data = mix_augmented(policy, aug, pool, partner_pool, tail, lam, za, zp)
+    data = mix_augmented(policy, aug, pool, partner_dev, tail, lam, za, zp)
     if timing is not None:
         timing["m1"] = torch.cuda.Event(enable_timing=True); timing["m1"].record()
-    return data, targets, all_targets[perm[lo:lo + b].to(all_targets.device)], lam
+    return data, targets, (all_targets[tgt_idx_dev] if all_targets.is_cuda else all_targets[perm[lo:lo + b]]), lam
 
 
 def mixup_global_allgather(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
