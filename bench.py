@@ -300,7 +300,8 @@ def measure_mixup(args, rank, world, barrier, max_over_ranks):
     Device-timed like the main metric."""
     import torch
     from fast_autoaugment_b200 import archive
-    from fast_autoaugment_b200.distributed import mixup_global
+    import torch.distributed as dist
+    from fast_autoaugment_b200.distributed import PeerPool, mixup_global, mixup_global_peer
     from fast_autoaugment_b200.engine import CompiledPolicy, TailSpec
     H = W = 224
     G = 2048
@@ -311,6 +312,26 @@ def measure_mixup(args, rank, world, barrier, max_over_ranks):
     y = torch.arange(rank * b, (rank + 1) * b, device="cuda")
     steps = max(10, min(args.steps, 50))
     tim = {}
+    # world > 1: the exchange is fused into the mix kernel (partners read over NVLink peer memory); FAA_MIXUP_A2A=1 or a
+    # failing peer mapping selects the NCCL all-to-all route
+    peer_pool, route = None, "local"
+    if world > 1:
+        route = "nccl_all_to_all"
+        if os.environ.get("FAA_MIXUP_A2A", "0") != "1":
+            try:
+                peer_pool = PeerPool(b, H, W, torch.device("cuda", torch.cuda.current_device()))
+                route = "nvlink_peer_loads"
+            except Exception as e:                      # noqa: BLE001 - report and fall back
+                sys.stderr.write("[bench] peer pool unavailable (%s): NCCL all-to-all route\n" % e)
+        flag = torch.tensor([1.0 if peer_pool is not None else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # all ranks or none
+        if float(flag.item()) == 0.0:
+            peer_pool, route = None, "nccl_all_to_all"
+
+    def mixup_global(pol_, x_, y_, tail_, alpha_, seed_, step_, timing=None, _a2a=mixup_global):
+        if peer_pool is not None:
+            return mixup_global_peer(pol_, x_, y_, tail_, alpha_, seed_, step_, peer_pool, timing=timing)
+        return _a2a(pol_, x_, y_, tail_, alpha_, seed_, step_, timing=timing)
     for i in range(3):
         mixup_global(pol, xs[i % 2], y, tail, 0.2, args.seed, i)
     barrier()
@@ -338,8 +359,11 @@ def measure_mixup(args, rank, world, barrier, max_over_ranks):
             "value": G * steps / (ms / 1e3), "unit": "images/s", "steps": steps, "ms_per_step": ms / steps, "scaling": "strong",
             "phases_ms": {"augment_to_u8": aug_ms, "exchange": ex_ms, "mix": mix_ms,
                           "note": "device time between events around each phase; the rest of ms_per_step is host / gaps"},
-            "exchange": {"kind": "partner-only all-to-all of the augmented uint8 images (NCCL all_to_all_single) + all-gather of the labels"
+            "exchange": {"kind": ("partner images read over NVLink peer memory inside the mix kernel (CUDA IPC mapped buffers, one tiny "
+                                  "all-reduce as the step barrier) + all-gather of the labels" if route == "nvlink_peer_loads" else
+                                  "partner-only all-to-all of the augmented uint8 images (NCCL all_to_all_single) + all-gather of the labels")
                                  if world > 1 else "none (single GPU: every partner is local)",
+                         "route": route,
                          "ms_per_step": ex_ms, "nvlink_bytes_received_per_gpu_per_step": recv,
                          "whole_pool_allgather_bytes_per_gpu_per_step": (world - 1) * b * H * W * 3},
             "roofline": {"bound": "hbm", "achieved": alg / world / (ms / steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s",

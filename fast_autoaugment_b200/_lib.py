@@ -72,6 +72,12 @@ def _load():
         "faa_augment_host": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), P(Rng), vp]),
         "faa_mixup": (C.c_int, [vp, vp, vp, C.c_int, i64, C.c_int, f32, f32, vp]),
         "faa_mix_u8": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), f32, f32, vp]),
+        "faa_enable_peer_access": (C.c_int, [C.c_int]),
+        "faa_peer_alloc": (C.c_int, [C.c_size_t, P(C.c_void_p), vp]),
+        "faa_peer_open": (C.c_int, [vp, P(C.c_void_p)]),
+        "faa_peer_close": (C.c_int, [vp]),
+        "faa_peer_free": (C.c_int, [vp]),
+        "faa_mix_u8_peer": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, P(Tail), f32, f32, vp]),
         "faa_color_jitter": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
         "faa_policy_set_lighting": (C.c_int, [vp, vp, C.c_int]),
         "faa_launch_count": (u64, []),

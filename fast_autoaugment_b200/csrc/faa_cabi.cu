@@ -1134,6 +1134,71 @@ int faa_mix_u8(faa_policy_t* p, const uint8_t* d_a, const uint8_t* d_b, const in
     return FAA_OK;
 }
 
+int faa_enable_peer_access(int peer_device) {
+    if (int e = ensure_device()) return e;
+    int dev = -1, can = 0;
+    CK(cudaGetDevice(&dev));
+    if (peer_device == dev) return FAA_OK;
+    CK(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return fail(FAA_ERR_UNSUPPORTED, "device " + std::to_string(dev) + " cannot access the memory of device " + std::to_string(peer_device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return FAA_OK; }
+    CK(e);
+    return FAA_OK;
+}
+
+// ---- buffers other processes of the node can map (CUDA IPC): the Mixup partner pool -------------------------------
+int faa_peer_alloc(size_t bytes, void** d_ptr, unsigned char* handle64) {
+    if (!d_ptr || !handle64 || bytes == 0) return fail(FAA_ERR_VALUE, "bad argument");
+    if (int e = ensure_device()) return e;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    if (cudaError_t e = cudaIpcGetMemHandle(&h, p)) { cudaFree(p); CK(e); }
+    CK(cudaMemset(p, 0, bytes));
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return FAA_OK;
+}
+
+int faa_peer_open(const unsigned char* handle64, void** d_ptr) {
+    if (!d_ptr || !handle64) return fail(FAA_ERR_VALUE, "bad argument");
+    if (int e = ensure_device()) return e;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    // opened under the CURRENT device: lazy peer access lets this device's kernels dereference the mapping
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FAA_OK;
+}
+
+int faa_peer_close(void* d_ptr) { if (d_ptr) CK(cudaIpcCloseMemHandle(d_ptr)); return FAA_OK; }
+int faa_peer_free(void* d_ptr) { if (d_ptr) CK(cudaFree(d_ptr)); return FAA_OK; }
+
+int faa_mix_u8_peer(faa_policy_t* p, const uint8_t* d_a, const uint8_t* const* d_partner_ptrs, const int16_t* d_zero_box_a,
+                    const int16_t* d_zero_box_b, void* d_out, int batch, int h, int w, const faa_tail_t* tail, float lam,
+                    float one_minus_lam, void* stream) {
+    if (!p || ((!d_a || !d_partner_ptrs || !d_out) && batch > 0)) return fail(FAA_ERR_VALUE, "null argument");
+    if (batch < 0) return fail(FAA_ERR_VALUE, "negative batch");
+    if (int e = check_shape(h, w)) return e;
+    if (int e = check_tail(tail)) return e;
+    if (tail->out_dtype == FAA_U8_HWC) return fail(FAA_ERR_UNSUPPORTED, "mixup needs a float output");
+    if (tail->out_h != h || tail->out_w != w) return fail(FAA_ERR_VALUE, "the augmented images already have the output size");
+    if ((w & 3) || ((uintptr_t)d_a & 3) || ((uintptr_t)d_out & 15) || ((uintptr_t)d_partner_ptrs & 7))
+        return fail(FAA_ERR_UNSUPPORTED, "faa_mix_u8_peer needs W % 4 == 0 and aligned buffers");
+    if (!(lam >= 0.0f && lam <= 1.0f)) return fail(FAA_ERR_MAGNITUDE, "lam must be in [0, 1]");   // aug_mixup.py:20
+    if (int e = ensure_device()) return e;
+    if (batch == 0) return FAA_OK;
+    if (int e = bind_device(p)) return e;
+    std::lock_guard<std::mutex> call_lk(p->call_mu);
+    AugParams dummy; bool tab = false;
+    if (int e = normalisation(p, tail, dummy, tab, (cudaStream_t)stream)) return e;
+    CK(launch_mix_u8(d_a, nullptr, nullptr, d_zero_box_a, d_zero_box_b, p->d_norm, d_out, batch, h, w, tail->out_dtype, lam,
+                     one_minus_lam, (cudaStream_t)stream, d_partner_ptrs));
+    g_launches++;
+    return FAA_OK;
+}
+
 int faa_mixup(const void* d_data, void* d_out, const int64_t* d_perm, int batch, int64_t n_per_sample, int dtype,
               float lam, float one_minus_lam, void* stream) {
     if ((!d_data || !d_out || !d_perm) && batch > 0) return fail(FAA_ERR_VALUE, "null argument");

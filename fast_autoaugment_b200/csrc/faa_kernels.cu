@@ -1990,6 +1990,9 @@ struct MixU8Params {
     const uint8_t* a;            // [batch][H][W][3]
     const uint8_t* b;            // partner pool [nb][H][W][3]
     const int32_t* partner;      // [batch] index into b
+    const uint8_t* const* b_ptrs;  // optional [batch]: the partner IMAGE of every sample (may be another GPU's memory, mapped
+                                 // through NVLink peer access: the exchange happens inside this kernel's loads); then zb_b is
+                                 // indexed per sample and b / partner are unused
     const int16_t* zb_a;         // [batch][4] zero boxes (y0, y1, x0, x1; half-open) or nullptr
     const int16_t* zb_b;         // [nb][4] or nullptr
     const float* norm_tab;       // [3][256] exact ToTensor+Normalize values
@@ -2009,10 +2012,11 @@ __global__ void __launch_bounds__(256) faa_mix_u8_kernel(const __grid_constant__
     }
     __syncthreads();
     const float za_val = f_mul(0.0f, P.lam), zb_val = f_mul(0.0f, P.oml);     // a zeroed (CutoutDefault) value, scaled
-    const int img = blockIdx.y, pi = __ldg(P.partner + img);
+    const int img = blockIdx.y, pi = P.b_ptrs ? img : __ldg(P.partner + img);
     const uint32_t npx = (uint32_t)P.H * (uint32_t)P.W, nq = npx >> 2;
     const uint32_t* a = reinterpret_cast<const uint32_t*>(P.a + (size_t)img * npx * 3u);
-    const uint32_t* b = reinterpret_cast<const uint32_t*>(P.b + (size_t)pi * npx * 3u);
+    const uint32_t* b = P.b_ptrs ? reinterpret_cast<const uint32_t*>(__ldg(reinterpret_cast<const unsigned long long*>(P.b_ptrs) + img))
+                                 : reinterpret_cast<const uint32_t*>(P.b + (size_t)pi * npx * 3u);
     T* o = reinterpret_cast<T*>(P.out) + (size_t)img * npx * 3u;
     int za[4] = {0, 0, 0, 0}, zb[4] = {0, 0, 0, 0};
     if (P.zb_a) for (int k = 0; k < 4; ++k) za[k] = P.zb_a[img * 4 + k];
@@ -2065,9 +2069,10 @@ __global__ void __launch_bounds__(256) faa_mix_u8_kernel(const __grid_constant__
 
 cudaError_t launch_mix_u8(const uint8_t* a, const uint8_t* b, const int32_t* partner, const int16_t* zb_a, const int16_t* zb_b,
                           const float* norm_tab, void* out, int batch, int H, int W, int dtype, float lam, float oml,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const uint8_t* const* b_ptrs) {
     if (batch <= 0) return cudaSuccess;
     MixU8Params P; P.a = a; P.b = b; P.partner = partner; P.zb_a = zb_a; P.zb_b = zb_b; P.norm_tab = norm_tab; P.out = out;
+    P.b_ptrs = b_ptrs;
     P.H = H; P.W = W; P.lam = lam; P.oml = oml;
     const uint32_t nq = (uint32_t)H * (uint32_t)W / 4u;
     unsigned gx = (nq + 255u) / 256u;

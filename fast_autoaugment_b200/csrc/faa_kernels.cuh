@@ -96,7 +96,7 @@ cudaError_t launch_mixup(const void* data, void* out, const int64_t* perm, int b
 
 cudaError_t launch_mix_u8(const uint8_t* a, const uint8_t* b, const int32_t* partner, const int16_t* zb_a, const int16_t* zb_b,
                           const float* norm_tab, void* out, int batch, int H, int W, int dtype, float lam, float one_minus_lam,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const uint8_t* const* b_ptrs = nullptr);
 
 cudaError_t launch_color_jitter(const uint8_t* in, uint8_t* out, const void* recs, int batch, int H, int W, cudaStream_t stream);
 cudaError_t launch_lighting_tables(const float* rgb, float* tabs, int n, const float mean[3], const float std[3], cudaStream_t stream);

@@ -237,6 +237,117 @@ def mixup_global(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.
     return data, targets, (all_targets[tgt_idx_dev] if all_targets.is_cuda else all_targets[perm[lo:lo + b]]), lam
 
 
+class _RawCuda:
+    """zero-copy torch view of a raw device allocation (``__cuda_array_interface__``)"""
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerPool:
+    """Per-rank uint8 buffers ``[slots][b][H][W][3]`` that EVERY rank of the node can read: each rank allocates its own
+    (C ABI ``faa_peer_alloc``: cudaMalloc + cudaIpcGetMemHandle), the 64-byte handles are all-gathered and every rank maps
+    its peers' buffers under ITS device (``faa_peer_open``: cudaIpcOpenMemHandle with lazy peer access), so that its kernels
+    can dereference them over NVLink.  ``ptr(rank, slot)`` is the device address of that rank's buffer in THIS process."""
+
+    def __init__(self, b: int, h: int, w: int, device, group=None, slots: int = 2):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.b, self.h, self.w, self.slots = b, h, w, slots
+        self.img_bytes = h * w * 3
+        self.device = torch.device(device)
+        nbytes = slots * b * self.img_bytes
+        with torch.cuda.device(self.device):
+            ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+            _lib.check(_lib.lib.faa_peer_alloc(nbytes, C.byref(ptr), handle))
+            self._own = ptr.value
+            self.local = torch.as_tensor(_RawCuda(self._own, (slots, b, h, w, 3)), device=self.device)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (self.device.index, bytes(handle)), group=group)
+            self.base, self._opened = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.base.append(self._own)
+                    continue
+                peer_dev, hb = gathered[r]
+                _lib.check(_lib.lib.faa_enable_peer_access(int(peer_dev)))
+                p = C.c_void_p()
+                _lib.check(_lib.lib.faa_peer_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)))
+                self.base.append(p.value)
+                self._opened.append(p.value)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    def ptr(self, rank: int, slot: int) -> int:
+        return self.base[rank] + slot * self.b * self.img_bytes
+
+    def close(self, group=None):
+        """unmap the peers' buffers, then (after a barrier: nobody maps ours any more) free our own"""
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                _lib.lib.faa_peer_close(C.c_void_p(p))
+            self._opened = []
+            dist.barrier(group=group)
+            if self._own:
+                self.local = None
+                _lib.lib.faa_peer_free(C.c_void_p(self._own))
+                self._own = 0
+
+
+def mixup_global_peer(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
+                      seed: int, step: int, pool: PeerPool, group=None, timing=None):
+    """``mixup_global`` with the exchange fused into the mix kernel: every rank augments its shard into its slot of the
+    ``PeerPool``, ONE tiny all-reduce orders the ranks (partners' images complete), and ``faa_mix_u8_peer`` reads each
+    partner image straight from its owner's memory over NVLink - no all-to-all, no received copy.  Slot ``step % 2``: the
+    barrier of step N+1 also tells every rank that its peers are done reading the slot of step N.  Same values as
+    ``mixup_global``."""
+    rank, world = pool.rank, pool.world
+    b, h, w = local_u8.shape[0], local_u8.shape[1], local_u8.shape[2]
+    assert (b, h, w) == (pool.b, pool.h, pool.w)
+    n = b * world
+    dev = local_u8.device
+    perm, lam = global_pairing(n, alpha, seed, step)
+    lo, _ = shard_bounds(n, rank, world)
+    slot = step % pool.slots
+    mine = perm[lo:lo + b].to(torch.int64)
+    base = torch.tensor([pool.ptr(r, slot) for r in range(world)], dtype=torch.int64)
+    ptrs = base[mine // b] + (mine % b) * pool.img_bytes         # address of every sample's partner image
+    ptrs_dev = _PinnedRing.upload(ptrs, dev)
+    tgt_idx_dev = _PinnedRing.upload(mine, dev)
+    u8_tail = TailSpec(tail.out_size, tail.crop_pad, tail.hflip, tail.mean, tail.std, 0, torch.uint8)
+    rng = make_rng(seed, step * n + lo, tail)
+    rng.zero_box_len = 0
+    if timing is not None:
+        timing["a0"] = torch.cuda.Event(enable_timing=True); timing["a0"].record()
+    aug = augment_batch(policy, local_u8, u8_tail, rng=rng, out=pool.local[slot])
+    if timing is not None:
+        timing["ex0"] = torch.cuda.Event(enable_timing=True); timing["ex0"].record()
+    if world > 1:
+        dist.all_reduce(pool.flag, group=group)                  # every rank's augmentation of this step has run
+    all_targets = gather_pool(targets, group) if world > 1 else targets
+    if timing is not None:
+        timing["ex1"] = torch.cuda.Event(enable_timing=True); timing["ex1"].record()
+        timing["recv_bytes"] = int((mine // b != rank).sum()) * pool.img_bytes
+    za = zp = None
+    if tail.cutout > 0:
+        rec_s, _ = philox_records(policy, n, h, w, tail, seed, step * n, dev)
+        zb_all = rec_s[:, 8:16].contiguous().view(torch.int16)
+        za = zb_all[lo:lo + b].contiguous()
+        zp = zb_all.index_select(0, tgt_idx_dev)
+    t = tail.c_struct(h, w)
+    out = torch.empty((b, 3, h, w), dtype=tail.out_dtype, device=dev)
+    if timing is not None:
+        timing["m0"] = torch.cuda.Event(enable_timing=True); timing["m0"].record()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.faa_mix_u8_peer(policy.handle, aug.data_ptr(), ptrs_dev.data_ptr(),
+                                            za.data_ptr() if za is not None else None, zp.data_ptr() if zp is not None else None,
+                                            out.data_ptr(), b, h, w, C.byref(t), float(np.float32(lam)), float(np.float32(1 - lam)),
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    if timing is not None:
+        timing["m1"] = torch.cuda.Event(enable_timing=True); timing["m1"].record()
+    return out, targets, all_targets[tgt_idx_dev], lam
+
+
 def mixup_global_allgather(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
                            seed: int, step: int, group=None, samples=None, boxes=None):
     """The north star's baseline exchange: all-gather of the WHOLE raw pool (G times the bytes ``mixup_global``

@@ -211,6 +211,22 @@ int faa_mix_u8(faa_policy_t* p, const uint8_t* d_a, const uint8_t* d_b, const in
                const int16_t* d_zero_box_a, const int16_t* d_zero_box_b, void* d_out, int batch, int h, int w,
                const faa_tail_t* tail, float lam, float one_minus_lam, void* stream);
 
+/* ---- the same pass with the partner exchange INSIDE the kernel: d_partner_ptrs[i] (device array of `batch` pointers)
+ * is the address of sample i's partner image - local, or in the memory of another GPU of the node mapped into this
+ * process (CUDA IPC / symmetric memory; NVLink peer access enabled).  The partner's bytes travel over NVSwitch as the
+ * kernel's loads: no all-to-all, no staging copy.  The caller orders it behind the partners' augmentation (a barrier
+ * across the ranks) and keeps their buffers alive until it has run.  d_zero_box_b: one box PER SAMPLE (its partner's). */
+int faa_enable_peer_access(int peer_device);      /* cudaDeviceEnablePeerAccess from the current device (idempotent) */
+/* a device buffer that the other processes of the node can map (cudaMalloc + cudaIpcGetMemHandle; 64-byte handle),
+ * the mapping of such a buffer under the current device (cudaIpcOpenMemHandle, lazy peer access), and their release */
+int faa_peer_alloc(size_t bytes, void** d_ptr, unsigned char* handle64);
+int faa_peer_open(const unsigned char* handle64, void** d_ptr);
+int faa_peer_close(void* d_ptr);
+int faa_peer_free(void* d_ptr);
+int faa_mix_u8_peer(faa_policy_t* p, const uint8_t* d_a, const uint8_t* const* d_partner_ptrs,
+                    const int16_t* d_zero_box_a, const int16_t* d_zero_box_b, void* d_out, int batch, int h, int w,
+                    const faa_tail_t* tail, float lam, float one_minus_lam, void* stream);
+
 /* ---- ImageNet train chain pieces (data.py:60-73), "next" row N2 --------------------------------
  * torchvision ColorJitter(brightness, contrast, saturation) (data.py:65-69) on uint8 HWC images, in place
  * allowed (d_out == d_in): per image the ops of order[] (torch.randperm(4): 0 brightness, 1 contrast,

@@ -34,6 +34,23 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.synchronize()
     np.save(os.path.join(out_dir, "rank%d.npy" % rank), data.cpu().numpy())
     np.save(os.path.join(out_dir, "t2_%d.npy" % rank), t2.cpu().numpy())
+    # the peer route (exchange fused into the mix kernel through NVLink peer memory) over several steps and both slots,
+    # with CutoutDefault boxes: must equal the all-to-all route bit for bit
+    from fast_autoaugment_b200.distributed import PeerPool, mixup_global_peer
+    tail_c = TailSpec.imagenet(16, torch.float16)
+    print("[rank %d] all-to-all route done" % rank, file=sys.stderr, flush=True)
+    pool = PeerPool(hi - lo, 64, 64, x.device)
+    print("[rank %d] peer pool mapped" % rank, file=sys.stderr, flush=True)
+    ok = True
+    for step in range(5):
+        a, _, ta, lam_a = mixup_global(pol, x, y, tail_c, 0.2, seed=5, step=step)
+        torch.cuda.synchronize()
+        b, _, tb, lam_b = mixup_global_peer(pol, x, y, tail_c, 0.2, seed=5, step=step, pool=pool)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(a, b) and torch.equal(ta, tb) and lam_a == lam_b
+        print("[rank %d] step %d equal=%s" % (rank, step, ok), file=sys.stderr, flush=True)
+    np.save(os.path.join(out_dir, "peer_ok_%d.npy" % rank), np.array([ok]))
+    pool.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -59,6 +76,7 @@ def test_global_mixup_two_gpus(tmp_path):
     want = augment_batch(pol, batch, tail, rng=make_rng(11, 4 * n, tail), partner=perm, lam=lam).cpu().numpy()
     assert np.array_equal(got, want)
     assert np.array_equal(t2, perm.numpy())
+    assert all(bool(np.load(os.path.join(tmp_path, "peer_ok_%d.npy" % r))[0]) for r in range(2))
     plain = augment_batch(pol, batch, tail, rng=make_rng(11, 4 * n, tail))
     ref = (plain * np.float32(lam) + plain[perm.cuda()] * np.float32(1 - lam)).cpu().numpy()
     assert np.array_equal(want, ref)
