@@ -294,6 +294,17 @@ class PeerPool:
                 self._own = 0
 
 
+def partner_pointers(perm: torch.Tensor, rank: int, world: int, bases, img_bytes: int) -> torch.Tensor:
+    """Address of every local sample's partner image for the pairing ``perm`` (contiguous equal shards): sample i of rank
+    ``rank`` pairs with global sample ``p = perm[rank * b + i]``, which is image ``p % b`` of rank ``p // b``, whose buffer
+    starts at ``bases[p // b]`` (as mapped in THIS process).  int64 tensor [b]; host logic only."""
+    n = int(perm.numel())
+    b = n // world
+    mine = perm[rank * b:(rank + 1) * b].to(torch.int64).cpu()
+    base = torch.tensor([int(x) for x in bases], dtype=torch.int64)
+    return base[mine // b] + (mine % b) * int(img_bytes)
+
+
 def mixup_global_peer(policy: CompiledPolicy, local_u8: torch.Tensor, targets: torch.Tensor, tail: TailSpec, alpha: float,
                       seed: int, step: int, pool: PeerPool, group=None, timing=None):
     """``mixup_global`` with the exchange fused into the mix kernel: every rank augments its shard into its slot of the
@@ -310,8 +321,7 @@ def mixup_global_peer(policy: CompiledPolicy, local_u8: torch.Tensor, targets: t
     lo, _ = shard_bounds(n, rank, world)
     slot = step % pool.slots
     mine = perm[lo:lo + b].to(torch.int64)
-    base = torch.tensor([pool.ptr(r, slot) for r in range(world)], dtype=torch.int64)
-    ptrs = base[mine // b] + (mine % b) * pool.img_bytes         # address of every sample's partner image
+    ptrs = partner_pointers(perm, rank, world, [pool.ptr(r, slot) for r in range(world)], pool.img_bytes)
     ptrs_dev = _PinnedRing.upload(ptrs, dev)
     tgt_idx_dev = _PinnedRing.upload(mine, dev)
     u8_tail = TailSpec(tail.out_size, tail.crop_pad, tail.hflip, tail.mean, tail.std, 0, torch.uint8)

@@ -67,6 +67,19 @@ def _worker(rank, world, port, out_dir):
     assert torch.equal(torch.from_numpy(batch)[recv_global], recv)                      # ... under its global index
     assert pool2.shape[0] == b + sum(recv_counts) < n                                    # less than the whole pool
 
+    # peer route (exchange fused into the mix kernel): the pointer table addresses, for every local sample, its partner's
+    # image inside the owner's buffer.  Here the "mapped buffers" are offsets into the all-gathered pool.
+    from fast_autoaugment_b200.distributed import partner_pointers
+    img_bytes = 32 * 32 * 3
+    bases = [1000 + r * b * img_bytes for r in range(world)]              # rank r's buffer starts at bases[r]
+    ptrs = partner_pointers(perm, rank, world, bases, img_bytes)
+    assert ptrs.dtype == torch.int64 and ptrs.shape == (b,)
+    flat = torch.from_numpy(batch).reshape(-1)
+    for i in range(b):
+        off = int(ptrs[i]) - 1000
+        assert off % img_bytes == 0 and off // img_bytes == int(perm[lo + i])           # = the partner's global index
+        assert torch.equal(flat[off:off + img_bytes], torch.from_numpy(batch[int(perm[lo + i])]).reshape(-1))
+
     emu = set_emu_sigs(ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libfaa_emu.so")))
     norm = exact_norm_table(CIFAR_MEAN, CIFAR_STD)
     mine = emu_augment(emu, pol, batch[lo:hi], samples[lo:hi], boxes[lo:hi], tail, norm,
