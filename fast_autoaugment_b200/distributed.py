@@ -255,27 +255,55 @@ class PeerPool:
         self.img_bytes = h * w * 3
         self.device = torch.device(device)
         nbytes = slots * b * self.img_bytes
-        with torch.cuda.device(self.device):
-            ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
-            _lib.check(_lib.lib.faa_peer_alloc(nbytes, C.byref(ptr), handle))
-            self._own = ptr.value
-            self.local = torch.as_tensor(_RawCuda(self._own, (slots, b, h, w, 3)), device=self.device)
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, (self.device.index, bytes(handle)), group=group)
-            self.base, self._opened = [], []
-            for r in range(self.world):
-                if r == self.rank:
-                    self.base.append(self._own)
-                    continue
-                peer_dev, hb = gathered[r]
-                _lib.check(_lib.lib.faa_enable_peer_access(int(peer_dev)))
-                p = C.c_void_p()
-                _lib.check(_lib.lib.faa_peer_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)))
-                self.base.append(p.value)
-                self._opened.append(p.value)
-        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=group)
+        # every rank runs the SAME sequence of collectives whether or not its local CUDA calls succeed, so that a failure on
+        # one rank becomes an exception on all of them (and the caller's fallback) instead of a hang
+        self._own, self._opened, self.base, self.local = 0, [], [], None
+        err, hb = None, None
+        try:
+            with torch.cuda.device(self.device):
+                ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+                _lib.check(_lib.lib.faa_peer_alloc(nbytes, C.byref(ptr), handle))
+                self._own, hb = ptr.value, bytes(handle)
+                self.local = torch.as_tensor(_RawCuda(self._own, (slots, b, h, w, 3)), device=self.device)
+        except Exception as e:                                   # noqa: BLE001
+            err = e
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (self.device.index, hb), group=group)
+        if err is None and all(g[1] is not None for g in gathered):
+            try:
+                with torch.cuda.device(self.device):
+                    for r in range(self.world):
+                        if r == self.rank:
+                            self.base.append(self._own)
+                            continue
+                        peer_dev, peer_hb = gathered[r]
+                        _lib.check(_lib.lib.faa_enable_peer_access(int(peer_dev)))
+                        p = C.c_void_p()
+                        _lib.check(_lib.lib.faa_peer_open((C.c_ubyte * 64).from_buffer_copy(peer_hb), C.byref(p)))
+                        self.base.append(p.value)
+                        self._opened.append(p.value)
+                    self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+                    torch.cuda.synchronize(self.device)
+            except Exception as e:                               # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not allocate its exportable buffer")
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)         # (also the barrier: every mapping exists)
+        if not all(oks):
+            self._release(group)
+            raise RuntimeError("peer pool unavailable on rank(s) %s%s" % (
+                [r for r, ok in enumerate(oks) if not ok], ": %s" % err if err is not None else ""))
+
+    def _release(self, group=None):
+        for p in self._opened:
+            _lib.lib.faa_peer_close(C.c_void_p(p))
+        self._opened = []
+        dist.barrier(group=group)                                # nobody maps our buffer any more
+        if self._own:
+            self.local = None
+            _lib.lib.faa_peer_free(C.c_void_p(self._own))
+            self._own = 0
 
     def ptr(self, rank: int, slot: int) -> int:
         return self.base[rank] + slot * self.b * self.img_bytes
@@ -284,14 +312,7 @@ class PeerPool:
         """unmap the peers' buffers, then (after a barrier: nobody maps ours any more) free our own"""
         torch.cuda.synchronize(self.device)
         with torch.cuda.device(self.device):
-            for p in self._opened:
-                _lib.lib.faa_peer_close(C.c_void_p(p))
-            self._opened = []
-            dist.barrier(group=group)
-            if self._own:
-                self.local = None
-                _lib.lib.faa_peer_free(C.c_void_p(self._own))
-                self._own = 0
+            self._release(group)
 
 
 def partner_pointers(perm: torch.Tensor, rank: int, world: int, bases, img_bytes: int) -> torch.Tensor:

@@ -80,6 +80,13 @@ def _worker(rank, world, port, out_dir):
         assert off % img_bytes == 0 and off // img_bytes == int(perm[lo + i])           # = the partner's global index
         assert torch.equal(flat[off:off + img_bytes], torch.from_numpy(batch[int(perm[lo + i])]).reshape(-1))
 
+    # without a GPU the exportable pool cannot be allocated: EVERY rank must get the exception (the caller then falls
+    # back to the all-to-all route) - no rank may be left waiting in a collective
+    from fast_autoaugment_b200.distributed import PeerPool
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="peer pool unavailable"):
+            PeerPool(b, 32, 32, torch.device("cuda", 0))
+
     emu = set_emu_sigs(ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libfaa_emu.so")))
     norm = exact_norm_table(CIFAR_MEAN, CIFAR_STD)
     mine = emu_augment(emu, pol, batch[lo:hi], samples[lo:hi], boxes[lo:hi], tail, norm,
