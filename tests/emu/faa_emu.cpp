@@ -254,6 +254,23 @@ int faa_emu_classes(const void* ops_v, int n_op, const void* samples_v, const vo
     return 0;
 }
 
+// weight class of every image's program in a three-way split launch (faa_resolve_kernel): 2 light, 1 mid, 0 heavy.
+// `allow`: bit 0 materialisation chunk, bit 1 scratch image, bit 2 lean octet gathers (faa_cabi.cu sets 7 for the
+// headline geometry and then does NOT launch the cluster kernel: no program may be heavy)
+int faa_emu_weight_classes(const void* ops_v, int n_op, const void* samples_v, const void* boxes_v, int B, int H, int W,
+                           int out_w, int apply_tail, int allow, uint8_t* wc_out, uint8_t* cls_out) {
+    const OpRec* ops = (const OpRec*)ops_v;
+    const Sample* samples = (const Sample*)samples_v;
+    const Box* boxes = (const Box*)boxes_v;
+    for (int i = 0; i < B; ++i) {
+        Prog g;
+        build_prog(samples[i], boxes + (size_t)i * n_op, ops, n_op, 0, apply_tail, H, W, out_w, allow, g);
+        wc_out[i] = prog_is_light(g) ? 2 : prog_is_mid(g, allow) ? 1 : 0;
+        if (cls_out) cls_out[i] = g.cls;
+    }
+    return 0;
+}
+
 int faa_emu_philox(const void* ops_v, const double* probs, int n_sub, int n_op, const void* rng_v, int B, int H,
                    int W, int out_h, int out_w, void* samples_v, void* boxes_v) {
     const OpRec* ops = (const OpRec*)ops_v;
