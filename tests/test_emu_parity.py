@@ -186,3 +186,28 @@ def test_translate_accumulator_break(emu):
     seed_all(3)
     samples, boxes = pol.sample_parity(len(batch), 380, 380)
     assert np.array_equal(emu_augment(emu, pol, batch, samples, boxes), want)
+
+
+@pytest.mark.parametrize("shape,n,pol_name,cutout", [((224, 224), 512, "fa_resnet50_rimagenet", 0),
+                                                      ((380, 380), 256, "fa_resnet50_rimagenet", 16),
+                                                      ((32, 32), 512, "fa_reduced_cifar10", 16)])
+def test_full_size_configs_every_image_against_the_oracle(emu, shape, n, pol_name, cutout):
+    """BASELINE.json configs 2, 3, 5 at FULL size, every image: kernel arithmetic (host build) == the reference's PIL /
+    torchvision chain in fp32.  tests/test_gpu_parity.py::test_full_size_configs demands GPU == this host build for every
+    image of the same batches, samples and seeds - together: the GPU equals the oracle on the whole batch, not on a sample."""
+    H, W = shape
+    policies = getattr(archive, pol_name)()
+    pol = CompiledPolicy(policies)
+    mean, std = (CIFAR_MEAN, CIFAR_STD) if H == 32 else (IMAGENET_MEAN, IMAGENET_STD)
+    tail = TailSpec((32, 32), 4, True, mean, std, cutout, torch.float32) if H == 32 else \
+        TailSpec(None, 0, True, mean, std, cutout, torch.float32)
+    batch = synth_batch(n, shape, seed=H)                      # (the GPU test's batch, seed and sampler call)
+    seed_all(77)
+    samples, boxes = pol.sample_parity(n, H, W, tail)
+    got = emu_augment(emu, pol, batch, samples, boxes, tail, exact_norm_table(mean, std))
+    seed_all(77)
+    chain = pil_path.cifar_train_chain(policies, cutout) if H == 32 else \
+        pil_path.fixed_shape_chain(policies, mean, std, True, cutout)
+    want = pil_path.run_chain_on_batch(chain, batch).numpy()
+    bad = [i for i in range(n) if not np.array_equal(got[i], want[i])]
+    assert not bad, (shape, len(bad), bad[:5], [policies[samples[i]["sub"]] for i in bad[:5]])
